@@ -1,0 +1,186 @@
+/*
+ * mkssd_b200.h — C ABI of libmkssd_b200.so: the B200 (sm_100a) implementation of MetaKSSD's
+ * data-parallel hot path.  Plain pointers and sizes only; this is what the reference's host C
+ * code (or any FFI: cgo / JNI / ctypes) binds instead of its CPU loops.
+ *
+ * Reference (yhg926/MetaKSSD v2.21) interface replaced by each entry point:
+ *
+ *   mk_ctx_create            seq2co_global_var_initial()           iseq2comem.c:54-86
+ *                            + get_hashsz()                        command_dist.c:286-315
+ *                            (the .shuf permutation is what read_dim_shuffle_file() returns,
+ *                             command_shuffle.c:215-235)
+ *   mk_fastq_koc_*           mt_shortreads2koc() + write_fqkoc2files()
+ *                                                                  iseq2comem.c:657-727, 516-562
+ *                            (call sites command_dist.c:380,382)
+ *   mk_fasta_co_*            fasta2co() + wrt_co2cmpn_use_inn_subctx()
+ *                                                                  iseq2comem.c:218-315, 625-652
+ *                            (call sites command_dist.c:397-398)
+ *   mk_composite_*           the dictionary build + probe loop of get_species_abundance()
+ *                                                                  command_composite.c:535-566
+ *                            and (mk_composite_stats) the per-species order statistics of
+ *                                                                  command_composite.c:598-613
+ *
+ * Results are bit-identical to the reference run single-threaded (`-p 1`): same codes and
+ * counts, same on-disk (hash-slot) order, same per-component split.
+ *
+ * There is NO CPU fallback: every call needs a CUDA device and fails with MK_ERR_CUDA otherwise.
+ * All functions return 0 (MK_OK) or a negative MK_ERR_* code; mk_strerror() names it and
+ * mk_last_error() returns the last detailed message of the calling context.
+ * A context is bound to one device and must be used from one host thread at a time.
+ */
+#ifndef MKSSD_B200_H
+#define MKSSD_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MK_OK 0
+#define MK_ERR_ARG (-1)         /* bad argument (NULL, misaligned device pointer, ...)          */
+#define MK_ERR_PARAM (-2)       /* k/subk/L outside the reference's table range (get_hashsz err) */
+#define MK_ERR_CUDA (-3)        /* CUDA runtime failure / no device                              */
+#define MK_ERR_NOMEM (-4)
+#define MK_ERR_CROWDED (-5)     /* distinct codes > hashlimit: reference err() "the context
+                                   space is too crowd, try rerun the program using -k<k+1>"     */
+#define MK_ERR_LONG_LINE (-6)   /* FASTQ line >= 4095 bytes: fgets(…,4096) splitting in the
+                                   reference is input-buffer dependent; refused                 */
+#define MK_ERR_IO (-7)          /* popen/fopen/read failure                                      */
+#define MK_ERR_EMPTY_QUERY (-8) /* composite with 0 query codes (reference: modulo by zero)      */
+#define MK_ERR_UNSUPPORTED (-9)
+
+typedef struct mk_ctx mk_ctx;
+
+/* Derived sketch parameters, same values the reference computes (iseq2comem.c:54-86). */
+typedef struct mk_info {
+    int k, subk, drlevel;
+    int kmer_len;            /* TL = 2k                                                     */
+    int outctx;              /* half outer context = k - subk                               */
+    int dim_end;             /* a k-mer passes iff shuf[inner substring] < dim_end          */
+    uint32_t hashsize;       /* primer[4(k-L)-15]                                            */
+    uint32_t hashlimit;      /* (uint32)(hashsize * 0.6)                                     */
+    int component_num;       /* 16^(k-L-8) or 1                                              */
+    int comp_code_bits;      /* 4(k-L-8) or 0                                                */
+    int code_bits;           /* 4(k-L)                                                       */
+    int device;
+    int sm_count;
+} mk_info;
+
+/* A sketch in the reference's per-component on-disk layout: for component c,
+ * codes[c][0..n[c]) is exactly the content of "<i>.co.<c>" (uint32 = code >> comp_code_bits)
+ * and counts[c] the content of "<i>.co.<c>.a" (NULL for FASTA sketches).  Library-owned;
+ * release with mk_sketch_free(). */
+typedef struct mk_sketch {
+    int n_components;
+    uint64_t n_total;        /* sum of n[c]  (== write_fqkoc2files() return value)           */
+    uint64_t *n;
+    uint32_t **codes;
+    uint16_t **counts;
+} mk_sketch;
+
+/* Accumulated device timings (CUDA events on the context's stream), for bench/roofline. */
+typedef struct mk_profile {
+    double stream_kernel_ms;     /* k_stream_* launches (the dominant kernel)               */
+    uint64_t stream_kernel_launches;
+    uint64_t stream_kernel_bytes;/* text bytes those launches scanned                       */
+    double reduce_ms;            /* count accumulation + ordering + slot reconstruction     */
+    double composite_ms;
+    uint64_t kernel_launches;    /* every kernel launched by this context                   */
+    uint64_t h2d_bytes, d2h_bytes;
+} mk_profile;
+
+const char *mk_strerror(int code);
+const char *mk_last_error(const mk_ctx *ctx);
+int mk_device_count(void);
+
+/* shuf_perm: the 16^subk int32 permutation of the .shuf file (host memory). */
+int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int subk, int drlevel, int device);
+void mk_ctx_destroy(mk_ctx *ctx);
+int mk_ctx_info(const mk_ctx *ctx, mk_info *info);
+int mk_ctx_profile(mk_ctx *ctx, mk_profile *prof, int reset);
+int mk_ctx_synchronize(mk_ctx *ctx);
+
+/* ---- FASTQ with k-mer counts (`dist -A`) ------------------------------------------------ */
+/* d_text: device pointer (16-byte aligned, readable up to the next 16-byte boundary past
+ * nbytes) holding the whole decompressed FASTQ text.  Input stays in HBM. */
+int mk_fastq_koc_device(mk_ctx *ctx, const void *d_text, size_t nbytes, mk_sketch *out);
+/* h_text: host memory (pinned memory makes the copy asynchronous and faster); the H2D copy
+ * is chunked and overlapped with the kernels. */
+int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes, mk_sketch *out);
+/* Same as the reference call: reads `<pipecmd or "zcat -fc"> <path>` through popen(). */
+int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out);
+
+/* ---- FASTA genomes (`dist` without -A; MarkerDB-build sketching) ------------------------- */
+/* A batch of n_files FASTA texts concatenated in one buffer; file i is bytes
+ * [offsets[i], offsets[i+1]).  out[i] receives the sketch of file i (counts == NULL). */
+int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_t *offsets, int n_files, mk_sketch *out);
+int mk_fasta_co_host(mk_ctx *ctx, const void *h_text, const uint64_t *offsets, int n_files, mk_sketch *out);
+int mk_fasta_co_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out);
+
+void mk_sketch_free(mk_sketch *s);
+
+/* ---- composite --------------------------------------------------------------------------- */
+/* One (query, component) step of get_species_abundance(): for every species s and every
+ * MarkerDB code ref_codes[ref_index[s] .. ref_index[s+1]) present in
+ * qry_codes[qry_lo .. qry_hi), append that code's query count.  Results are ACCUMULATED into a
+ * library-owned per-context hit store so that components can be fed one after another
+ * (call mk_composite_begin first).  All pointers are host memory. */
+int mk_composite_begin(mk_ctx *ctx, int n_species);
+int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, int n_species,
+                           const uint32_t *qry_codes, const uint16_t *qry_counts, uint64_t qry_lo,
+                           uint64_t qry_hi);
+/* Per-species order statistics over the accumulated hits, the integers the reference prints
+ * (command_composite.c:598-624); the two float ratios are sum/n and lastsum/lastn. */
+typedef struct mk_species_stat {
+    int32_t n;          /* matched k-mers                                                   */
+    int32_t sum;        /* int sum of counts (32-bit wrap like the reference's int)        */
+    int32_t lastsum;    /* sum over the 98th..99th percentile window                        */
+    int32_t lastn;
+    int32_t median;     /* a[n/2] of the 1-based ascending array                            */
+    int32_t max;        /* a[n]                                                             */
+} mk_species_stat;
+int mk_composite_stats(mk_ctx *ctx, mk_species_stat *stats /* [n_species] */);
+/* Raw hit lists in reference layout: lists[s][0] = n, lists[s][1..n] = counts in MarkerDB code
+ * order (component-major).  Library-owned until the next mk_composite_begin/destroy. */
+int mk_composite_hits(mk_ctx *ctx, const int32_t *const **lists);
+
+/* ---- multi-GPU building blocks (one context per rank) ------------------------------------ */
+/* Rank-local partial sketch of a contiguous shard of the FASTQ text.  pos_base = global byte
+ * offset of the shard, line_base = number of '\n' bytes before it (its low 2 bits select the
+ * record phase), is_last = shard ends the file (trailing-partial-record rule applies).
+ * Produces device-resident runs sorted by code: (code u64, firstpos u64, count u32).
+ * The d_* pointers are library-owned and valid until the next call on this context. */
+typedef struct mk_runs {
+    uint64_t n;
+    const uint64_t *d_code;
+    const uint64_t *d_firstpos;
+    const uint32_t *d_count;
+} mk_runs;
+int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,
+                            int is_last, mk_runs *runs);
+/* Merge runs (possibly from several ranks, concatenated in device memory, any order): sum the
+ * counts per code with saturation at 65535, keep the minimum firstpos, then reproduce the
+ * reference's hash-slot order and split by component. */
+int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos, const uint32_t *d_count,
+                            uint64_t n, mk_sketch *out);
+/* Merge only (no ordering): device-resident reduced runs sorted by code. */
+int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos, const uint32_t *d_count,
+                         uint64_t n, mk_runs *merged);
+/* number of '\n' bytes in a device buffer (to derive line_base of the next shard) */
+int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t *count);
+
+/* ---- synthetic workload generator on the device (bench / tests; mkssd_synth.h) ----------- */
+struct mks_params;
+/* Writes FASTQ records [r0, r1) into d_out (capacity bytes); *written = bytes produced. */
+int mk_synth_fastq_device(mk_ctx *ctx, const struct mks_params *P, const uint32_t *cdf32, const uint32_t *cdf_species,
+                          uint64_t r0, uint64_t r1, void *d_out, size_t capacity, size_t *written);
+/* Writes the FASTA text of species [s0, s1) back to back; offsets[s1-s0+1] (host) receives the
+ * file boundaries. */
+int mk_synth_fasta_device(mk_ctx *ctx, const struct mks_params *P, uint32_t s0, uint32_t s1, void *d_out,
+                          size_t capacity, uint64_t *offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKSSD_B200_H */

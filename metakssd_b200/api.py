@@ -1,0 +1,405 @@
+"""ctypes binding of libmkssd_b200.so (include/mkssd_b200.h) and a thin host-side mirror of the
+reference's interface for the hot path:
+
+  reference (C, yhg926/MetaKSSD)                          here
+  ------------------------------------------------------  -----------------------------------------
+  read_dim_shuffle_file()      command_shuffle.c:215      read_shuf()
+  seq2co_global_var_initial()  iseq2comem.c:54            Sketcher(perm, k, subk, drlevel)
+  mt_shortreads2koc()+write_fqkoc2files()  :657 / :516    Sketcher.fastq_koc_{device,host,file}()
+  fasta2co()+wrt_co2cmpn_use_inn_subctx()  :218 / :625    Sketcher.fasta_co_{device,host}()
+  run_stageI() combine + cofiles.stat  command_dist.c:408 write_sketch_dir()
+  get_species_abundance()      command_composite.c:446    Sketcher.composite() / composite_tsv()
+
+The CUDA library is mandatory: importing works without a GPU (so that symbol/ABI checks can run
+on a CPU box), but every compute call raises MkError when no device is present — there is no CPU
+fallback and nothing here touches oracle/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import struct
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmkssd_b200.so")
+
+MK_OK = 0
+ERRORS = {
+    -1: "MK_ERR_ARG", -2: "MK_ERR_PARAM", -3: "MK_ERR_CUDA", -4: "MK_ERR_NOMEM", -5: "MK_ERR_CROWDED",
+    -6: "MK_ERR_LONG_LINE", -7: "MK_ERR_IO", -8: "MK_ERR_EMPTY_QUERY", -9: "MK_ERR_UNSUPPORTED",
+}
+
+
+class MkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("%s (%d): %s" % (ERRORS.get(code, "MK_ERR_?"), code, msg))
+        self.code = code
+
+
+class MkInfo(C.Structure):
+    _fields_ = [
+        ("k", C.c_int), ("subk", C.c_int), ("drlevel", C.c_int), ("kmer_len", C.c_int), ("outctx", C.c_int),
+        ("dim_end", C.c_int), ("hashsize", C.c_uint32), ("hashlimit", C.c_uint32), ("component_num", C.c_int),
+        ("comp_code_bits", C.c_int), ("code_bits", C.c_int), ("device", C.c_int), ("sm_count", C.c_int),
+    ]
+
+
+class MkSketch(C.Structure):
+    _fields_ = [
+        ("n_components", C.c_int), ("n_total", C.c_uint64), ("n", C.POINTER(C.c_uint64)),
+        ("codes", C.POINTER(C.POINTER(C.c_uint32))), ("counts", C.POINTER(C.POINTER(C.c_uint16))),
+    ]
+
+
+class MkProfile(C.Structure):
+    _fields_ = [
+        ("stream_kernel_ms", C.c_double), ("stream_kernel_launches", C.c_uint64),
+        ("stream_kernel_bytes", C.c_uint64), ("reduce_ms", C.c_double), ("composite_ms", C.c_double),
+        ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+    ]
+
+
+class MkSpeciesStat(C.Structure):
+    _fields_ = [("n", C.c_int32), ("sum", C.c_int32), ("lastsum", C.c_int32), ("lastn", C.c_int32),
+                ("median", C.c_int32), ("max", C.c_int32)]
+
+
+class MkRuns(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("d_code", C.c_void_p), ("d_firstpos", C.c_void_p), ("d_count", C.c_void_p)]
+
+
+class MksParams(C.Structure):  # include/mkssd_synth.h
+    _fields_ = [
+        ("seed", C.c_uint64), ("n_species", C.c_uint32), ("genome_len", C.c_uint32), ("read_len", C.c_uint32),
+        ("genus_size", C.c_uint32), ("shared_len", C.c_uint32), ("sub_thresh16", C.c_uint32),
+        ("n_thresh16", C.c_uint32), ("n_present", C.c_uint32),
+    ]
+
+
+# every symbol include/mkssd_b200.h declares
+EXPORTS = [
+    "mk_strerror", "mk_last_error", "mk_device_count", "mk_ctx_create", "mk_ctx_destroy", "mk_ctx_info",
+    "mk_ctx_profile", "mk_ctx_synchronize", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
+    "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
+    "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_fastq_partial_device",
+    "mk_runs_finalize_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
+    "mk_synth_fasta_device",
+]
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library.  Fails loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libmkssd_b200.so is missing: run `python -m metakssd_b200.build` "
+                          "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, u64, i32 = C.c_void_p, C.c_size_t, C.c_uint64, C.c_int
+    L.mk_strerror.restype = C.c_char_p
+    L.mk_strerror.argtypes = [i32]
+    L.mk_last_error.restype = C.c_char_p
+    L.mk_last_error.argtypes = [vp]
+    L.mk_device_count.restype = i32
+    L.mk_ctx_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32, i32]
+    L.mk_ctx_destroy.argtypes = [vp]
+    L.mk_ctx_destroy.restype = None
+    L.mk_ctx_info.argtypes = [vp, C.POINTER(MkInfo)]
+    L.mk_ctx_profile.argtypes = [vp, C.POINTER(MkProfile), i32]
+    L.mk_ctx_synchronize.argtypes = [vp]
+    L.mk_fastq_koc_device.argtypes = [vp, vp, sz, C.POINTER(MkSketch)]
+    L.mk_fastq_koc_host.argtypes = [vp, vp, sz, C.POINTER(MkSketch)]
+    L.mk_fastq_koc_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(MkSketch)]
+    L.mk_fasta_co_device.argtypes = [vp, vp, vp, i32, C.POINTER(MkSketch)]
+    L.mk_fasta_co_host.argtypes = [vp, vp, vp, i32, C.POINTER(MkSketch)]
+    L.mk_fasta_co_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(MkSketch)]
+    L.mk_sketch_free.argtypes = [C.POINTER(MkSketch)]
+    L.mk_sketch_free.restype = None
+    L.mk_composite_begin.argtypes = [vp, i32]
+    L.mk_composite_component.argtypes = [vp, vp, vp, i32, vp, vp, u64, u64]
+    L.mk_composite_stats.argtypes = [vp, vp]
+    L.mk_composite_hits.argtypes = [vp, C.POINTER(C.POINTER(C.POINTER(C.c_int32)))]
+    L.mk_fastq_partial_device.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
+    L.mk_runs_finalize_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkSketch)]
+    L.mk_runs_merge_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkRuns)]
+    L.mk_count_newlines_device.argtypes = [vp, vp, sz, C.POINTER(u64)]
+    L.mk_synth_fastq_device.argtypes = [vp, C.POINTER(MksParams), vp, vp, u64, u64, vp, sz, C.POINTER(sz)]
+    L.mk_synth_fasta_device.argtypes = [vp, C.POINTER(MksParams), C.c_uint32, C.c_uint32, vp, sz, vp]
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return int(load().mk_device_count())
+
+
+# ------------------------------------------------------------------------------------ .shuf files
+def read_shuf(path: str):
+    """(shuf_id, k, subk, drlevel, int32 permutation) — format of command_shuffle.c:164-235."""
+    with open(path, "rb") as f:
+        hdr = f.read(16)
+        shuf_id, k, subk, drlevel = struct.unpack("<iiii", hdr)
+        perm = np.fromfile(f, dtype=np.int32, count=1 << (4 * subk))
+    if perm.size != 1 << (4 * subk):
+        raise ValueError("truncated .shuf file %s" % path)
+    return shuf_id, k, subk, drlevel, perm
+
+
+def write_shuf(path: str, shuf_id: int, k: int, subk: int, drlevel: int, perm: np.ndarray) -> None:
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iiii", shuf_id, k, subk, drlevel))
+        f.write(np.ascontiguousarray(perm, dtype=np.int32).tobytes())
+
+
+# ------------------------------------------------------------------------------------ results
+@dataclass
+class Sketch:
+    """Per-component arrays exactly as the reference writes `<i>.co.<c>` / `<i>.co.<c>.a`."""
+    codes: list            # [component] -> uint32[]
+    counts: list | None    # [component] -> uint16[]   (None for FASTA sketches)
+
+    @property
+    def n_total(self) -> int:
+        return int(sum(c.size for c in self.codes))
+
+
+def _take_sketch(sk: MkSketch, with_counts: bool) -> Sketch:
+    codes, counts = [], ([] if with_counts else None)
+    for c in range(sk.n_components):
+        n = int(sk.n[c])
+        codes.append(np.ctypeslib.as_array(sk.codes[c], shape=(n,)).copy() if n else np.empty(0, np.uint32))
+        if with_counts:
+            counts.append(np.ctypeslib.as_array(sk.counts[c], shape=(n,)).copy() if n else np.empty(0, np.uint16))
+    load().mk_sketch_free(C.byref(sk))
+    return Sketch(codes, counts)
+
+
+def _ptr(x) -> int:
+    """Device pointer of a torch tensor / raw int, host pointer of a numpy array."""
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    raise TypeError(type(x))
+
+
+class Sketcher:
+    """One sketching context bound to one GPU (mk_ctx)."""
+
+    def __init__(self, perm: np.ndarray, k: int, subk: int, drlevel: int, device: int = 0):
+        self._L = load()
+        self._h = C.c_void_p()
+        perm = np.ascontiguousarray(perm, dtype=np.int32)
+        if perm.size != 1 << (4 * subk):
+            raise ValueError("permutation must have 16^subk entries")
+        rc = self._L.mk_ctx_create(C.byref(self._h), perm.ctypes.data, k, subk, drlevel, device)
+        if rc != MK_OK:
+            self._h = C.c_void_p()
+            raise MkError(rc, self._L.mk_strerror(rc).decode())
+        self.info = MkInfo()
+        self._L.mk_ctx_info(self._h, C.byref(self.info))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._L.mk_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc: int):
+        if rc != MK_OK:
+            raise MkError(rc, self._L.mk_last_error(self._h).decode() or self._L.mk_strerror(rc).decode())
+
+    def profile(self, reset: bool = False) -> MkProfile:
+        p = MkProfile()
+        self._ck(self._L.mk_ctx_profile(self._h, C.byref(p), 1 if reset else 0))
+        return p
+
+    # -- FASTQ -A
+    def fastq_koc_device(self, d_text, nbytes: int) -> Sketch:
+        sk = MkSketch()
+        self._ck(self._L.mk_fastq_koc_device(self._h, _ptr(d_text), nbytes, C.byref(sk)))
+        return _take_sketch(sk, True)
+
+    def fastq_koc_host(self, text) -> Sketch:
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else text
+        sk = MkSketch()
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, dtype=np.uint8)
+            self._ck(self._L.mk_fastq_koc_host(self._h, a.ctypes.data, a.size, C.byref(sk)))
+        else:  # pinned torch CPU tensor
+            self._ck(self._L.mk_fastq_koc_host(self._h, int(a.data_ptr()), int(a.numel()), C.byref(sk)))
+        return _take_sketch(sk, True)
+
+    def fastq_koc_file(self, path: str, pipecmd: str = "") -> Sketch:
+        sk = MkSketch()
+        self._ck(self._L.mk_fastq_koc_file(self._h, path.encode(), pipecmd.encode(), C.byref(sk)))
+        return _take_sketch(sk, True)
+
+    # -- FASTA
+    def fasta_co_device(self, d_text, offsets) -> list:
+        off = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = off.size - 1
+        arr = (MkSketch * n)()
+        self._ck(self._L.mk_fasta_co_device(self._h, _ptr(d_text), off.ctypes.data, n, arr))
+        return [_take_sketch(arr[i], False) for i in range(n)]
+
+    def fasta_co_host(self, texts) -> list:
+        """texts: list of byte strings / uint8 arrays, one per FASTA file."""
+        arrs = [np.frombuffer(t, dtype=np.uint8) if isinstance(t, (bytes, bytearray)) else
+                np.ascontiguousarray(t, dtype=np.uint8) for t in texts]
+        off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([a.size for a in arrs])
+        buf = np.concatenate(arrs) if arrs else np.empty(0, np.uint8)
+        n = len(arrs)
+        arr = (MkSketch * n)()
+        self._ck(self._L.mk_fasta_co_host(self._h, buf.ctypes.data, off.ctypes.data, n, arr))
+        return [_take_sketch(arr[i], False) for i in range(n)]
+
+    def fasta_co_file(self, path: str, pipecmd: str = "") -> Sketch:
+        sk = MkSketch()
+        self._ck(self._L.mk_fasta_co_file(self._h, path.encode(), pipecmd.encode(), C.byref(sk)))
+        return _take_sketch(sk, False)
+
+    # -- composite
+    def composite(self, ref_comp, qry_comp, want_lists: bool = False):
+        """ref_comp: per component (codes uint32[], index uint64[S+1]); qry_comp: per component
+        (codes uint32[], counts uint16[]) of ONE query.  Returns the per-species stats array
+        (structured: n,sum,lastsum,lastn,median,max) and, optionally, the raw hit lists."""
+        S = int(ref_comp[0][1].size - 1)
+        self._ck(self._L.mk_composite_begin(self._h, S))
+        for (rc, ri), (qc, qa) in zip(ref_comp, qry_comp):
+            rc = np.ascontiguousarray(rc, dtype=np.uint32)
+            ri = np.ascontiguousarray(ri, dtype=np.uint64)
+            qc = np.ascontiguousarray(qc, dtype=np.uint32)
+            qa = np.ascontiguousarray(qa, dtype=np.uint16)
+            self._ck(self._L.mk_composite_component(self._h, rc.ctypes.data, ri.ctypes.data, S, qc.ctypes.data,
+                                                    qa.ctypes.data, 0, qc.size))
+        stats = np.zeros(S, dtype=np.dtype([("n", "<i4"), ("sum", "<i4"), ("lastsum", "<i4"), ("lastn", "<i4"),
+                                            ("median", "<i4"), ("max", "<i4")]))
+        self._ck(self._L.mk_composite_stats(self._h, stats.ctypes.data))
+        if not want_lists:
+            return stats
+        lists = C.POINTER(C.POINTER(C.c_int32))()
+        self._ck(self._L.mk_composite_hits(self._h, C.byref(lists)))
+        out = []
+        for s in range(S):
+            n = lists[s][0]
+            out.append(np.ctypeslib.as_array(lists[s], shape=(n + 1,)).copy())
+        return stats, out
+
+    # -- multi-GPU building blocks
+    def fastq_partial_device(self, d_text, nbytes: int, pos_base: int, line_base: int, is_last: bool) -> MkRuns:
+        r = MkRuns()
+        self._ck(self._L.mk_fastq_partial_device(self._h, _ptr(d_text), nbytes, pos_base, line_base,
+                                                 1 if is_last else 0, C.byref(r)))
+        return r
+
+    def runs_finalize_device(self, d_code, d_pos, d_cnt, n: int) -> Sketch:
+        sk = MkSketch()
+        self._ck(self._L.mk_runs_finalize_device(self._h, _ptr(d_code), _ptr(d_pos), _ptr(d_cnt), n, C.byref(sk)))
+        return _take_sketch(sk, True)
+
+    def runs_merge_device(self, d_code, d_pos, d_cnt, n: int) -> MkRuns:
+        r = MkRuns()
+        self._ck(self._L.mk_runs_merge_device(self._h, _ptr(d_code), _ptr(d_pos), _ptr(d_cnt), n, C.byref(r)))
+        return r
+
+    def count_newlines_device(self, d_text, nbytes: int) -> int:
+        v = C.c_uint64()
+        self._ck(self._L.mk_count_newlines_device(self._h, _ptr(d_text), nbytes, C.byref(v)))
+        return int(v.value)
+
+    # -- synthetic workload on the device
+    def synth_fastq_device(self, P: MksParams, cdf32: np.ndarray, species: np.ndarray, r0: int, r1: int, d_out,
+                           capacity: int) -> int:
+        w = C.c_size_t()
+        cdf32 = np.ascontiguousarray(cdf32, dtype=np.uint32)
+        species = np.ascontiguousarray(species, dtype=np.uint32)
+        self._ck(self._L.mk_synth_fastq_device(self._h, C.byref(P), cdf32.ctypes.data, species.ctypes.data, r0, r1,
+                                               _ptr(d_out), capacity, C.byref(w)))
+        return int(w.value)
+
+    def synth_fasta_device(self, P: MksParams, s0: int, s1: int, d_out, capacity: int) -> np.ndarray:
+        off = np.zeros(s1 - s0 + 1, dtype=np.uint64)
+        self._ck(self._L.mk_synth_fasta_device(self._h, C.byref(P), s0, s1, _ptr(d_out), capacity, off.ctypes.data))
+        return off
+
+
+# ------------------------------------------------------------------------------------ host mirror
+CO_DSTAT = struct.Struct("<I?3xiiiiQ")  # co_dstat_t, global_basic.h:116-126
+
+
+def write_sketch_dir(path: str, shuf_id: int, info: MkInfo, names, sketches, koc: bool) -> None:
+    """What run_stageI() leaves on disk (command_dist.c:408-500): combco.<c>, combco.<c>.a,
+    combco.index.<c> and cofiles.stat, for `sketches[i]` of input `names[i]`."""
+    os.makedirs(path, exist_ok=True)
+    cn = info.component_num
+    ctx_ct = np.array([s.n_total for s in sketches], dtype=np.uint32)
+    for c in range(cn):
+        idx = np.zeros(len(sketches) + 1, dtype=np.uint64)
+        idx[1:] = np.cumsum([s.codes[c].size for s in sketches])
+        with open(os.path.join(path, "combco.%d" % c), "wb") as f:
+            for s in sketches:
+                f.write(s.codes[c].astype(np.uint32).tobytes())
+        idx.tofile(os.path.join(path, "combco.index.%d" % c))
+        if koc:
+            with open(os.path.join(path, "combco.%d.a" % c), "wb") as f:
+                for s in sketches:
+                    f.write(s.counts[c].astype(np.uint16).tobytes())
+    with open(os.path.join(path, "cofiles.stat"), "wb") as f:
+        f.write(CO_DSTAT.pack(shuf_id & 0xFFFFFFFF, bool(koc), 2 * info.k, 2 * info.drlevel, cn, len(sketches),
+                              int(ctx_ct.sum())))
+        f.write(ctx_ct.tobytes())
+        for n in names:
+            b = n.encode()[:255]
+            f.write(b + b"\0" * (256 - len(b)))
+
+
+def read_sketch_dir(path: str):
+    """(header dict, names, per-component combco, index, abund|None)"""
+    raw = open(os.path.join(path, "cofiles.stat"), "rb").read()
+    shuf_id, koc, kmerlen, dim_rd_len, comp_num, infile_num, all_ctx = CO_DSTAT.unpack_from(raw, 0)
+    off = CO_DSTAT.size + 4 * infile_num
+    names = [raw[off + 256 * i: off + 256 * (i + 1)].split(b"\0", 1)[0].decode() for i in range(infile_num)]
+    combco = [np.fromfile(os.path.join(path, "combco.%d" % c), dtype=np.uint32) for c in range(comp_num)]
+    index = [np.fromfile(os.path.join(path, "combco.index.%d" % c), dtype=np.uint64) for c in range(comp_num)]
+    abund = [np.fromfile(os.path.join(path, "combco.%d.a" % c), dtype=np.uint16) for c in range(comp_num)] if koc else None
+    hdr = dict(shuf_id=shuf_id, koc=bool(koc), kmerlen=kmerlen, dim_rd_len=dim_rd_len, comp_num=comp_num,
+               infile_num=infile_num, all_ctx_ct=all_ctx)
+    return hdr, names, combco, index, abund
+
+
+def composite_tsv(qry_name: str, ref_names, stats) -> str:
+    """species_coverage lines exactly as command_composite.c:582-624 prints them: species ordered
+    by matched k-mers (descending, ties by index as glibc's stable qsort leaves them), stopping at
+    the first with fewer than MIN_KM_S = 6; ratios are computed in float32 and printed with %f."""
+    order = np.argsort(-stats["n"].astype(np.int64), kind="stable")
+    lines = []
+    for s in order:
+        n = int(stats["n"][s])
+        if n < 6:
+            break
+        mean = np.float32(np.int32(stats["sum"][s])) / np.float32(n)
+        last = np.float32(np.int32(stats["lastsum"][s])) / np.float32(int(stats["lastn"][s]))
+        lines.append("%s\t%s\t%d\t%f\t%f\t%d\t%d\n" % (qry_name, ref_names[s], n, float(mean), float(last),
+                                                     int(stats["median"][s]), int(stats["max"][s])))
+    return "".join(lines)

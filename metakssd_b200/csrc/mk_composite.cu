@@ -1,0 +1,274 @@
+// mk_composite.cu — MarkerDB intersection of `metakssd composite`.
+//
+// Replaces the dictionary build + probe loop of get_species_abundance()
+// (/root/reference/command_composite.c:535-566) and the per-species order statistics of
+// command_composite.c:598-613.  Only membership matters for the result (the reference's own
+// 32-bit wrap-around probe arithmetic is an implementation detail of its dictionary), so the query
+// codes go into a device hash and every MarkerDB code is probed by one thread; hits are compacted
+// in MarkerDB order (component-major) into a per-context store.  Statistics: one radix sort of
+// (species << 16 | count) and one thread per species.
+#include "mk_common.cuh"
+
+#define EMPTY64 0xFFFFFFFFFFFFFFFFull
+
+__device__ __forceinline__ u32 mixc(u32 x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+k_cq_insert(const u32 *__restrict__ qry, u64 q, u64 *__restrict__ keys, u32 *__restrict__ idxmin, u32 mask)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= q) return;
+    u64 key = qry[i];
+    u32 h = mixc((u32)key) & mask;
+    for (;;) {
+        u64 old = atomicCAS((unsigned long long *)&keys[h], EMPTY64, key);
+        if (old == EMPTY64 || old == key) break;
+        h = (h + 1) & mask;
+    }
+    atomicMin(&idxmin[h], (u32)i); // a duplicated query code resolves to its first occurrence (:537-545)
+}
+
+__global__ void __launch_bounds__(256)
+k_cq_probe(const u32 *__restrict__ ref, u64 r, const u64 *__restrict__ keys, const u32 *__restrict__ idxmin, u32 mask,
+           const uint16_t *__restrict__ qcnt, u32 *__restrict__ flag, u32 *__restrict__ val)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r) return;
+    u64 key = ref[i];
+    u32 h = mixc((u32)key) & mask;
+    u32 f = 0, v = 0;
+    for (;;) {
+        u64 k = keys[h];
+        if (k == EMPTY64) break;
+        if (k == key) { f = 1; v = qcnt[idxmin[h]]; break; }
+        h = (h + 1) & mask;
+    }
+    flag[i] = f;
+    val[i] = v;
+}
+
+__global__ void __launch_bounds__(256)
+k_cq_gather(const u32 *__restrict__ flag, const u32 *__restrict__ val, const u32 *__restrict__ pos, u64 r,
+            const u64 *__restrict__ ref_index, int n_species, u32 *__restrict__ store_s, u32 *__restrict__ store_c,
+            u64 store_base)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r || !flag[i]) return;
+    int lo = 0, hi = n_species - 1; // species s with ref_index[s] <= i < ref_index[s+1]
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (ref_index[mid] <= i) lo = mid; else hi = mid - 1;
+    }
+    u64 o = store_base + pos[i];
+    store_s[o] = (u32)lo;
+    store_c[o] = val[i];
+}
+
+extern "C" int mk_composite_begin(mk_ctx *ctx, int n_species)
+{
+    if (!ctx || n_species <= 0) return MK_ERR_ARG;
+    ctx->comp_species = n_species;
+    ctx->comp_nhits = 0;
+    ctx->comp_lists_flat.clear();
+    ctx->comp_lists_ptr.clear();
+    return MK_OK;
+}
+
+extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, int n_species,
+                                      const uint32_t *qry_codes, const uint16_t *qry_counts, uint64_t qry_lo,
+                                      uint64_t qry_hi)
+{
+    if (!ctx || !ref_index || n_species != ctx->comp_species || qry_hi < qry_lo) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const u64 q = qry_hi - qry_lo;
+    // the reference sizes its dictionary with nextPrime((int)(q / 0.6)); 0 or 1 make it divide by zero
+    if ((int)((double)q / 0.6) <= 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "composite: query sketch has %llu codes", (unsigned long long)q);
+        return MK_ERR_EMPTY_QUERY;
+    }
+    const u64 r = ref_index[n_species];
+    if (r == 0) return MK_OK;
+    if (r >= 0xFFFFFFFFull || q >= 0x7FFFFFFFull) return MK_ERR_UNSUPPORTED;
+    cudaEvent_t e0 = ctx->ev2, e1 = ctx->ev3;
+    CK(cudaEventRecord(e0, ctx->stream));
+    u32 *d_ref, *d_qry, *d_flag, *d_val, *d_pos, *d_idx, *store_s, *store_c;
+    u64 *d_index, *d_keys;
+    uint16_t *d_qcnt;
+    CKR(mk_scratch(ctx, SB_C_REF, (size_t)r, &d_ref));
+    CKR(mk_scratch(ctx, SB_C_IDX, (size_t)n_species + 1, &d_index));
+    CKR(mk_scratch(ctx, SB_C_QRY, (size_t)q, &d_qry));
+    CKR(mk_scratch(ctx, SB_C_QCNT, (size_t)q, &d_qcnt));
+    CKR(mk_scratch(ctx, SB_C_HITVAL, (size_t)2 * r, &d_flag));
+    d_val = d_flag + r;
+    CKR(mk_scratch(ctx, SB_C_POS, (size_t)r, &d_pos));
+    u64 cap = 1024;
+    while (cap < 2 * q) cap <<= 1;
+    CKR(mk_scratch(ctx, SB_CQ_KEYS, (size_t)cap, &d_keys));
+    CKR(mk_scratch(ctx, SB_CQ_IDX, (size_t)cap, &d_idx));
+    // grow the hit store, keeping what earlier components appended
+    {
+        u64 need = ctx->comp_nhits + r;
+        Scratch &ss = ctx->sb[SB_C_STORE_S], &sc = ctx->sb[SB_C_STORE_C];
+        if (ss.bytes < need * 4 || sc.bytes < need * 4) {
+            u32 *ns, *nc;
+            size_t bytes = (size_t)(need + need / 2) * 4 + 256;
+            CK(cudaMalloc(&ns, bytes));
+            CK(cudaMalloc(&nc, bytes));
+            if (ctx->comp_nhits) {
+                CK(cudaMemcpyAsync(ns, ss.p, ctx->comp_nhits * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(nc, sc.p, ctx->comp_nhits * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                CK(cudaStreamSynchronize(ctx->stream));
+            }
+            if (ss.p) cudaFree(ss.p);
+            if (sc.p) cudaFree(sc.p);
+            ss.p = ns; ss.bytes = bytes;
+            sc.p = nc; sc.bytes = bytes;
+        }
+        store_s = (u32 *)ss.p;
+        store_c = (u32 *)sc.p;
+    }
+    CK(cudaMemcpyAsync(d_ref, ref_codes, (size_t)r * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_index, ref_index, (size_t)(n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_qry, qry_codes + qry_lo, (size_t)q * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_qcnt, qry_counts + qry_lo, (size_t)q * 2, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof.h2d_bytes += r * 4 + (u64)(n_species + 1) * 8 + q * 6;
+    CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(d_idx, 0xFF, (size_t)cap * 4, ctx->stream));
+    k_cq_insert<<<(unsigned)((q + 255) / 256), 256, 0, ctx->stream>>>(d_qry, q, d_keys, d_idx, (u32)(cap - 1));
+    LAUNCH_COUNT(ctx);
+    k_cq_probe<<<(unsigned)((r + 255) / 256), 256, 0, ctx->stream>>>(d_ref, r, d_keys, d_idx, (u32)(cap - 1), d_qcnt,
+                                                                    d_flag, d_val);
+    LAUNCH_COUNT(ctx);
+    u64 nh = 0;
+    CKR(mk_exclusive_scan_u32(ctx, d_flag, d_pos, r, &nh));
+    k_cq_gather<<<(unsigned)((r + 255) / 256), 256, 0, ctx->stream>>>(d_flag, d_val, d_pos, r, d_index, n_species,
+                                                                     store_s, store_c, ctx->comp_nhits);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    ctx->prof.composite_ms += ms;
+    ctx->comp_nhits += nh;
+    return MK_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_cstat_keys(const u32 *__restrict__ store_s, const u32 *__restrict__ store_c, u64 n, u64 *__restrict__ keys,
+             u64 *__restrict__ vals)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = ((u64)store_s[i] << 16) | (store_c[i] & 0xFFFFu);
+        vals[i] = i;
+    }
+}
+
+// element j of the reference's 1-based array: a[0] = n, a[j] = j-th smallest count
+__device__ __forceinline__ int ref_elem(const u64 *__restrict__ keys, u64 lo, int n, int j)
+{
+    return j == 0 ? n : (int)(keys[lo + (u64)j - 1] & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(128)
+k_cstat(const u64 *__restrict__ keys, u64 n, int n_species, mk_species_stat *__restrict__ out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_species) return;
+    // [lo, hi) = entries of species s in the sorted keys
+    u64 a = 0, b = n;
+    while (a < b) { u64 m = (a + b) >> 1; if ((keys[m] >> 16) < (u64)s) a = m + 1; else b = m; }
+    u64 lo = a;
+    b = n;
+    while (a < b) { u64 m = (a + b) >> 1; if ((keys[m] >> 16) <= (u64)s) a = m + 1; else b = m; }
+    u64 hi = a;
+    int cnt = (int)(hi - lo);
+    mk_species_stat st;
+    st.n = cnt;
+    u32 sum = 0;
+    for (u64 i = lo; i < hi; i++) sum += (u32)(keys[i] & 0xFFFFu);
+    st.sum = (int32_t)sum;
+    u32 lastsum = 0;
+    int lastn = 0;
+    int j0 = (int)(cnt * 0.98);
+    for (int j = j0; (double)j <= cnt * 0.99; j++) { lastsum += (u32)ref_elem(keys, lo, cnt, j); lastn++; }
+    st.lastsum = (int32_t)lastsum;
+    st.lastn = lastn;
+    st.median = cnt ? ref_elem(keys, lo, cnt, cnt / 2) : 0;
+    st.max = cnt ? ref_elem(keys, lo, cnt, cnt) : 0;
+    out[s] = st;
+}
+
+extern "C" int mk_composite_stats(mk_ctx *ctx, mk_species_stat *stats)
+{
+    if (!ctx || !stats || ctx->comp_species <= 0) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int S = ctx->comp_species;
+    const u64 n = ctx->comp_nhits;
+    if (n == 0) {
+        memset(stats, 0, sizeof(mk_species_stat) * (size_t)S);
+        return MK_OK;
+    }
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    u64 *k0, *v0, *k1, *v1;
+    mk_species_stat *d_out;
+    CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n, &k0));
+    CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n, &v0));
+    CKR(mk_scratch(ctx, SB_SORT_K1, (size_t)n, &k1));
+    CKR(mk_scratch(ctx, SB_SORT_V1, (size_t)n, &v1));
+    CKR(mk_scratch(ctx, SB_C_STATS, (size_t)S, &d_out));
+    k_cstat_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const u32 *)ctx->sb[SB_C_STORE_S].p,
+                                                                      (const u32 *)ctx->sb[SB_C_STORE_C].p, n, k0, v0);
+    LAUNCH_COUNT(ctx);
+    int sb = 0;
+    for (u64 v = (u64)(S - 1); v; v >>= 1) sb++;
+    u64 *sk = k0, *sv = v0;
+    CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, 16 + sb));
+    k_cstat<<<(S + 127) / 128, 128, 0, ctx->stream>>>(sk, n, S, d_out);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(stats, d_out, sizeof(mk_species_stat) * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev3, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3));
+    ctx->prof.composite_ms += ms;
+    ctx->prof.d2h_bytes += sizeof(mk_species_stat) * (u64)S;
+    return MK_OK;
+}
+
+extern "C" int mk_composite_hits(mk_ctx *ctx, const int32_t *const **lists)
+{
+    if (!ctx || !lists || ctx->comp_species <= 0) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int S = ctx->comp_species;
+    const u64 n = ctx->comp_nhits;
+    std::vector<u32> hs(n), hc(n);
+    if (n) {
+        CK(cudaMemcpyAsync(hs.data(), ctx->sb[SB_C_STORE_S].p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hc.data(), ctx->sb[SB_C_STORE_C].p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->prof.d2h_bytes += n * 8;
+    }
+    std::vector<u64> cnt((size_t)S + 1, 0);
+    for (u64 i = 0; i < n; i++) cnt[hs[i] + 1]++;
+    // layout: for species s, [n_s, v_1 .. v_n_s]
+    std::vector<u64> start((size_t)S + 1, 0);
+    for (int s = 0; s < S; s++) start[s + 1] = start[s] + 1 + cnt[s + 1];
+    ctx->comp_lists_flat.assign((size_t)start[S], 0);
+    std::vector<u64> fill((size_t)S, 0);
+    for (int s = 0; s < S; s++) ctx->comp_lists_flat[start[s]] = (int32_t)cnt[s + 1];
+    for (u64 i = 0; i < n; i++) {
+        u32 s = hs[i];
+        ctx->comp_lists_flat[start[s] + 1 + fill[s]++] = (int32_t)hc[i];
+    }
+    ctx->comp_lists_ptr.resize((size_t)S);
+    for (int s = 0; s < S; s++) ctx->comp_lists_ptr[s] = ctx->comp_lists_flat.data() + start[s];
+    *lists = ctx->comp_lists_ptr.data();
+    return MK_OK;
+}

@@ -1,0 +1,481 @@
+// mk_reduce.cu — from (code, position) candidates to the reference's on-disk sketch.
+//
+// Replaces the open-addressing table of mt_shortreads2koc()/fasta2co()
+// (/root/reference/iseq2comem.c:701-717, :295-310) and the slot-order dump of
+// write_fqkoc2files()/wrt_co2cmpn_use_inn_subctx() (iseq2comem.c:539-553, :637-645):
+//
+//   1. count accumulation: a global-memory hash (atomicCAS insert, atomicAdd count, atomicMin of
+//      the first position) keyed by (file, code);
+//   2. first-occurrence ranking: radix sort of the distinct codes by first position — this is the
+//      order in which a single-threaded reference run inserts them;
+//   3. slot reconstruction: the reference writes codes in ascending slot of a double-hashing table
+//      of `hashsize` entries.  Sequential insertion "rank r takes the first slot of its probe
+//      sequence not held by a smaller rank" is the unique fix-point of a parallel scheme where every
+//      slot keeps the minimum rank that claimed it (atomicMin) and an evicted rank resumes probing
+//      from its next step.  The table is kept sparse (slot -> rank map sized by the number of
+//      codes), so cost does not depend on hashsize (268 MB / 4.3 GB dense in the reference);
+//   4. radix sort by (file, component, slot) and emission of uint32 codes / uint16 counts.
+#include "mk_common.cuh"
+#include <limits.h>
+
+#define EMPTY64 0xFFFFFFFFFFFFFFFFull
+#define EMPTY32 0xFFFFFFFFu
+
+__device__ __forceinline__ u64 mix64(u64 x)
+{
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__global__ void k_fill_u64(u64 *p, u64 n, u64 v)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_u32(u32 *p, u64 n, u32 v)
+{
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---- 1. accumulate -----------------------------------------------------------------------------
+// cand_cnt == nullptr: every candidate counts 1 (fresh k-mer occurrences);
+// otherwise candidates are partial runs carrying their own (already saturated) count.
+__global__ void __launch_bounds__(256)
+k_acc_insert(const u64 *__restrict__ cand_code, const u64 *__restrict__ cand_pos, const u32 *__restrict__ cand_cnt,
+             u64 n, long long keep_below, const u64 *__restrict__ file_off, int n_files, int TL, int code_bits,
+             u64 *__restrict__ keys, u32 *__restrict__ cnt, u64 *__restrict__ minpos, u64 mask)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 pos = cand_pos[i];
+    if ((long long)pos >= keep_below) return;
+    u64 file = 0;
+    if (file_off) {
+        int lo = 0, hi = n_files - 1; // largest f with file_off[f] <= pos
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (file_off[mid] <= pos) lo = mid; else hi = mid - 1;
+        }
+        file = (u64)lo;
+        if (pos + 1 < file_off[lo] + (u64)TL) return; // k-mer would start before this file's first base
+    }
+    u64 key = (file << code_bits) | cand_code[i];
+    u64 h = mix64(key) & mask;
+    for (;;) {
+        u64 old = atomicCAS((unsigned long long *)&keys[h], EMPTY64, key);
+        if (old == EMPTY64 || old == key) break;
+        h = (h + 1) & mask;
+    }
+    u32 add = cand_cnt ? cand_cnt[i] : 1u;
+    atomicAdd(&cnt[h], add);
+    atomicMin((unsigned long long *)&minpos[h], pos);
+}
+
+__global__ void __launch_bounds__(256)
+k_acc_compact(const u64 *__restrict__ keys, const u32 *__restrict__ cnt, const u64 *__restrict__ minpos, u64 cap,
+              int code_bits, int drop_zero_code, u64 *__restrict__ out_key, u32 *__restrict__ out_cnt,
+              u64 *__restrict__ out_pos, u64 *__restrict__ out_n)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    bool occ = false;
+    u64 key = 0;
+    if (i < cap) {
+        key = keys[i];
+        occ = key != EMPTY64;
+        if (occ && drop_zero_code && (key & ((1ull << code_bits) - 1)) == 0) occ = false;
+    }
+    u32 m = __ballot_sync(0xffffffffu, occ);
+    if (!m) return;
+    u32 lane = threadIdx.x & 31;
+    u64 base = 0;
+    if (lane == 0) base = atomicAdd((unsigned long long *)out_n, (unsigned long long)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (occ) {
+        u64 o = base + __popc(m & ((1u << lane) - 1u));
+        out_key[o] = key;
+        out_cnt[o] = cnt[i];
+        out_pos[o] = minpos[i];
+    }
+}
+
+static inline u64 pow2_at_least(u64 v)
+{
+    u64 p = 1024;
+    while (p < v) p <<= 1;
+    return p;
+}
+static inline int bit_length(u64 v)
+{
+    int b = 0;
+    while (v) { b++; v >>= 1; }
+    return b;
+}
+
+static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u32 *d_cnt, u64 n, long long keep_below,
+                      const u64 *d_file_off, int n_files, int code_bits, bool drop_zero, u64 **d_it_key, u32 **d_it_cnt,
+                      u64 **d_it_pos, u64 *n_items)
+{
+    *n_items = 0;
+    u64 cap = pow2_at_least(2 * n + 2);
+    u64 *keys, *minpos, *it_key, *it_pos, *counters;
+    u32 *cnt, *it_cnt;
+    CKR(mk_scratch(ctx, SB_ACC_KEYS, (size_t)cap, &keys));
+    CKR(mk_scratch(ctx, SB_ACC_CNT, (size_t)cap, &cnt));
+    CKR(mk_scratch(ctx, SB_ACC_POS, (size_t)cap, &minpos));
+    CKR(mk_scratch(ctx, SB_IT_CODE, (size_t)n + 1, &it_key));
+    CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n + 1, &it_cnt));
+    CKR(mk_scratch(ctx, SB_IT_POS, (size_t)n + 1, &it_pos));
+    CKR(mk_scratch(ctx, SB_COUNTERS, 8, &counters));
+    CK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(minpos, 0xFF, (size_t)cap * 8, ctx->stream));
+    CK(cudaMemsetAsync(cnt, 0, (size_t)cap * 4, ctx->stream));
+    CK(cudaMemsetAsync(counters + 4, 0, 8, ctx->stream));
+    if (n) {
+        k_acc_insert<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_code, d_pos, d_cnt, n, keep_below, d_file_off,
+                                                                         n_files, ctx->kp.TL, code_bits, keys, cnt,
+                                                                         minpos, cap - 1);
+        LAUNCH_COUNT(ctx);
+    }
+    k_acc_compact<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(keys, cnt, minpos, cap, code_bits,
+                                                                        drop_zero ? 1 : 0, it_key, it_cnt, it_pos,
+                                                                        counters + 4);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(n_items, counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.d2h_bytes += 8;
+    *d_it_key = it_key;
+    *d_it_cnt = it_cnt;
+    *d_it_pos = it_pos;
+    return MK_OK;
+}
+
+int mk_reduce_candidates(mk_ctx *ctx, const u64 *d_cand_code, const u64 *d_cand_pos, u64 n_cand, long long keep_below,
+                         const u64 *d_file_off, int n_files, int code_bits, u64 **d_it_key, u32 **d_it_cnt,
+                         u64 **d_it_pos, u64 *n_items)
+{
+    return accumulate(ctx, d_cand_code, d_cand_pos, nullptr, n_cand, keep_below, d_file_off, n_files, code_bits,
+                      d_file_off != nullptr, d_it_key, d_it_cnt, d_it_pos, n_items);
+}
+
+// ---- 2./3. ranking and slot reconstruction -----------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_make_rank_keys(const u64 *__restrict__ it_pos, u64 n, u64 *__restrict__ keys, u64 *__restrict__ vals)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = it_pos[i]; vals[i] = i; }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_ranked(const u64 *__restrict__ perm, u64 n, const u64 *__restrict__ it_key, const u32 *__restrict__ it_cnt,
+                u64 *__restrict__ r_key, u32 *__restrict__ r_cnt)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        u64 s = perm[i];
+        r_key[i] = it_key[s];
+        r_cnt[i] = it_cnt[s];
+    }
+}
+
+__device__ __forceinline__ u32 probe_slot(u64 code, u64 i, u64 hs)
+{
+    // global_basic.h:282-284 — 64-bit arithmetic
+    return (u32)((code % hs + i * (1ull + code % (hs - 1ull))) % hs);
+}
+
+__global__ void __launch_bounds__(256)
+k_slot_assign(const u64 *__restrict__ r_key, u64 n, int code_bits, u64 hs, u64 *__restrict__ slot_keys,
+              u32 *__restrict__ slot_vals, u64 smask, u32 *probe_i)
+{
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u64 cmask = (code_bits >= 64) ? ~0ull : ((1ull << code_bits) - 1);
+    u32 carry = (u32)r;
+    u64 i = 0;
+    for (;;) {
+        u64 key = r_key[carry];
+        u64 file = key >> code_bits, code = key & cmask;
+        u32 slot = probe_slot(code, i, hs);
+        u64 skey = (file << 32) | slot;
+        u64 h = mix64(skey) & smask;
+        for (;;) {
+            u64 old = atomicCAS((unsigned long long *)&slot_keys[h], EMPTY64, skey);
+            if (old == EMPTY64 || old == skey) break;
+            h = (h + 1) & smask;
+        }
+        ((volatile u32 *)probe_i)[carry] = (u32)i;
+        __threadfence();
+        u32 old = atomicMin(&slot_vals[h], carry);
+        if (old == EMPTY32) break;           // free slot: placed
+        if (old > carry) {                   // evicted a later rank: it resumes from its next probe step
+            __threadfence();
+            i = (u64)((volatile u32 *)probe_i)[old] + 1;
+            carry = old;
+        } else {
+            i++;                             // held by an earlier rank
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_make_out_keys(const u64 *__restrict__ r_key, const u32 *__restrict__ probe_i, u64 n, int code_bits, u64 hs,
+                u32 comp_mask, int sbits, int cbits, u64 *__restrict__ keys, u64 *__restrict__ vals)
+{
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const u64 cmask = (code_bits >= 64) ? ~0ull : ((1ull << code_bits) - 1);
+    u64 key = r_key[r];
+    u64 file = key >> code_bits, code = key & cmask;
+    u32 slot = probe_slot(code, probe_i[r], hs);
+    u64 comp = code & comp_mask;
+    keys[r] = (file << (sbits + cbits)) | (comp << sbits) | slot;
+    vals[r] = r;
+}
+
+__global__ void __launch_bounds__(256)
+k_emit(const u64 *__restrict__ skeys, const u64 *__restrict__ perm, u64 n, const u64 *__restrict__ r_key,
+       const u32 *__restrict__ r_cnt, int code_bits, int comp_code_bits, int sbits, u32 *__restrict__ out_code,
+       uint16_t *__restrict__ out_cnt, u64 *__restrict__ seg_start)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u64 cmask = (code_bits >= 64) ? ~0ull : ((1ull << code_bits) - 1);
+    u64 r = perm[i];
+    u64 code = r_key[r] & cmask;
+    out_code[i] = (u32)(code >> comp_code_bits);
+    u32 c = r_cnt[r];
+    out_cnt[i] = (uint16_t)(c > 65535u ? 65535u : c);
+    u64 seg = skeys[i] >> sbits;
+    if (i == 0 || (skeys[i - 1] >> sbits) != seg) seg_start[seg] = i;
+}
+
+int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, u64 n, int n_files, bool with_counts,
+                      bool drop_zero_code, mk_sketch *out)
+{
+    (void)drop_zero_code;
+    const mk_info &I = ctx->info;
+    const int cn = I.component_num;
+    const int code_bits = I.code_bits;
+    // initialise outputs (also for n == 0)
+    for (int f = 0; f < n_files; f++) {
+        mk_sketch *s = &out[f];
+        s->n_components = cn;
+        s->n_total = 0;
+        s->n = (uint64_t *)calloc((size_t)cn, sizeof(uint64_t));
+        s->codes = (uint32_t **)calloc((size_t)cn, sizeof(uint32_t *));
+        s->counts = with_counts ? (uint16_t **)calloc((size_t)cn, sizeof(uint16_t *)) : nullptr;
+        if (!s->n || !s->codes || (with_counts && !s->counts)) return MK_ERR_NOMEM;
+    }
+    if (n == 0) return MK_OK;
+    if (n >= 0xFFFFFFF0ull) return MK_ERR_UNSUPPORTED;
+
+    const u64 nb = (n + 255) / 256;
+    u64 *k0, *v0, *k1, *v1;
+    CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n, &k0));
+    CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n, &v0));
+    CKR(mk_scratch(ctx, SB_SORT_K1, (size_t)n, &k1));
+    CKR(mk_scratch(ctx, SB_SORT_V1, (size_t)n, &v1));
+
+    // rank by first position
+    k_make_rank_keys<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_it_pos, n, k0, v0);
+    LAUNCH_COUNT(ctx);
+    u64 *sk = k0, *sv = v0;
+    CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, ctx->pos_bits)); // bits of the largest position
+    u64 *r_key;
+    u32 *r_cnt, *probe_i;
+    CKR(mk_scratch(ctx, SB_R_CODE, (size_t)n, &r_key));
+    CKR(mk_scratch(ctx, SB_R_CNT, (size_t)n, &r_cnt));
+    CKR(mk_scratch(ctx, SB_R_PROBE, (size_t)n, &probe_i));
+    k_gather_ranked<<<(unsigned)nb, 256, 0, ctx->stream>>>(sv, n, d_it_key, d_it_cnt, r_key, r_cnt);
+    LAUNCH_COUNT(ctx);
+
+    // sparse slot map
+    u64 scap = pow2_at_least(2 * n + 2);
+    u64 *slot_keys;
+    u32 *slot_vals;
+    CKR(mk_scratch(ctx, SB_SLOT_KEYS, (size_t)scap, &slot_keys));
+    CKR(mk_scratch(ctx, SB_SLOT_VALS, (size_t)scap, &slot_vals));
+    CK(cudaMemsetAsync(slot_keys, 0xFF, (size_t)scap * 8, ctx->stream));
+    CK(cudaMemsetAsync(slot_vals, 0xFF, (size_t)scap * 4, ctx->stream));
+    k_slot_assign<<<(unsigned)nb, 256, 0, ctx->stream>>>(r_key, n, code_bits, (u64)I.hashsize, slot_keys, slot_vals,
+                                                        scap - 1, probe_i);
+    LAUNCH_COUNT(ctx);
+
+    // order by (file, component, slot)
+    int sbits = bit_length((u64)I.hashsize);
+    int cbits = bit_length((u64)cn - 1);
+    int fbits = bit_length((u64)(n_files > 1 ? n_files - 1 : 0));
+    if (sbits + cbits + fbits > 64) return MK_ERR_UNSUPPORTED;
+    k_make_out_keys<<<(unsigned)nb, 256, 0, ctx->stream>>>(r_key, probe_i, n, code_bits, (u64)I.hashsize, (u32)(cn - 1),
+                                                          sbits, cbits, k0, v0);
+    LAUNCH_COUNT(ctx);
+    sk = k0; sv = v0;
+    CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, sbits + cbits + fbits));
+
+    u32 *out_code;
+    uint16_t *out_cnt;
+    u64 *seg_start;
+    const u64 nseg = (u64)n_files << cbits;
+    CKR(mk_scratch(ctx, SB_OUT_CODE, (size_t)n, &out_code));
+    CKR(mk_scratch(ctx, SB_OUT_CNT, (size_t)n, &out_cnt));
+    CKR(mk_scratch(ctx, SB_SEG_COUNTS, (size_t)nseg + 1, &seg_start));
+    CK(cudaMemsetAsync(seg_start, 0xFF, (size_t)(nseg + 1) * 8, ctx->stream));
+    k_emit<<<(unsigned)nb, 256, 0, ctx->stream>>>(sk, sv, n, r_key, r_cnt, code_bits, I.comp_code_bits, sbits, out_code,
+                                                 out_cnt, seg_start);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+
+    std::vector<u64> h_seg(nseg + 1);
+    std::vector<uint32_t> h_code(n);
+    std::vector<uint16_t> h_cnt(with_counts ? n : 0);
+    CK(cudaMemcpyAsync(h_seg.data(), seg_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_code.data(), out_code, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (with_counts) CK(cudaMemcpyAsync(h_cnt.data(), out_cnt, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.d2h_bytes += nseg * 8 + n * 4 + (with_counts ? n * 2 : 0);
+    // empty segments inherit the start of the next non-empty one
+    h_seg[nseg] = n;
+    for (long long s = (long long)nseg - 1; s >= 0; s--)
+        if (h_seg[s] == EMPTY64) h_seg[s] = h_seg[s + 1];
+    for (int f = 0; f < n_files; f++) {
+        mk_sketch *s = &out[f];
+        for (int c = 0; c < cn; c++) {
+            u64 seg = ((u64)f << cbits) | (u64)c;
+            u64 lo = h_seg[seg], hi = h_seg[seg + 1];
+            u64 m = hi - lo;
+            s->n[c] = m;
+            s->n_total += m;
+            s->codes[c] = (uint32_t *)malloc((size_t)(m ? m : 1) * 4);
+            if (!s->codes[c]) return MK_ERR_NOMEM;
+            memcpy(s->codes[c], h_code.data() + lo, (size_t)m * 4);
+            if (with_counts) {
+                s->counts[c] = (uint16_t *)malloc((size_t)(m ? m : 1) * 2);
+                if (!s->counts[c]) return MK_ERR_NOMEM;
+                memcpy(s->counts[c], h_cnt.data() + lo, (size_t)m * 2);
+            }
+        }
+        if (s->n_total > I.hashlimit) {
+            snprintf(ctx->err, sizeof(ctx->err),
+                     "the context space is too crowd, try rerun the program using -k%d", I.k + 1);
+            return MK_ERR_CROWDED;
+        }
+    }
+    return MK_OK;
+}
+
+int mk_finalize_candidates(mk_ctx *ctx, const u64 *d_cand_code, const u64 *d_cand_pos, u64 n_cand, long long keep_below,
+                           const u64 *d_file_off, int n_files, bool with_counts, mk_sketch *out)
+{
+    u64 *it_key, *it_pos, n_items;
+    u32 *it_cnt;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    CKR(mk_reduce_candidates(ctx, d_cand_code, d_cand_pos, n_cand, keep_below, d_file_off, n_files, ctx->info.code_bits,
+                             &it_key, &it_cnt, &it_pos, &n_items));
+    int rc = mk_order_and_emit(ctx, it_key, it_cnt, it_pos, n_items, n_files, with_counts, d_file_off != nullptr, out);
+    cudaEventRecord(ctx->ev3, ctx->stream);
+    cudaEventSynchronize(ctx->ev3);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.reduce_ms += ms;
+    return rc;
+}
+
+// ---- multi-GPU building blocks -----------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_split_runs(const u64 *__restrict__ perm, const u64 *__restrict__ skeys, u64 n, const u32 *__restrict__ it_cnt,
+             const u64 *__restrict__ it_pos, u64 *__restrict__ o_code, u64 *__restrict__ o_pos, u32 *__restrict__ o_cnt)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 s = perm[i];
+    o_code[i] = skeys[i];
+    o_pos[i] = it_pos[s];
+    u32 c = it_cnt[s];
+    o_cnt[i] = c > 65535u ? 65535u : c;
+}
+
+static int runs_sorted_by_code(mk_ctx *ctx, u64 *it_key, u32 *it_cnt, u64 *it_pos, u64 n, mk_runs *runs)
+{
+    runs->n = n;
+    runs->d_code = nullptr; runs->d_firstpos = nullptr; runs->d_count = nullptr;
+    if (n == 0) return MK_OK;
+    const u64 nb = (n + 255) / 256;
+    u64 *k0, *v0, *k1, *v1, *o_code, *o_pos;
+    u32 *o_cnt;
+    CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n, &k0));
+    CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n, &v0));
+    CKR(mk_scratch(ctx, SB_SORT_K1, (size_t)n, &k1));
+    CKR(mk_scratch(ctx, SB_SORT_V1, (size_t)n, &v1));
+    CKR(mk_scratch(ctx, SB_RUN_CODE, (size_t)n, &o_code));
+    CKR(mk_scratch(ctx, SB_RUN_POS, (size_t)n, &o_pos));
+    CKR(mk_scratch(ctx, SB_RUN_CNT, (size_t)n, &o_cnt));
+    k_make_rank_keys<<<(unsigned)nb, 256, 0, ctx->stream>>>(it_key, n, k0, v0);
+    LAUNCH_COUNT(ctx);
+    u64 *sk = k0, *sv = v0;
+    CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, ctx->info.code_bits));
+    k_split_runs<<<(unsigned)nb, 256, 0, ctx->stream>>>(sv, sk, n, it_cnt, it_pos, o_code, o_pos, o_cnt);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    runs->d_code = (const uint64_t *)o_code; runs->d_firstpos = (const uint64_t *)o_pos; runs->d_count = o_cnt;
+    return MK_OK;
+}
+
+extern "C" int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t pos_base,
+                                       uint64_t line_base, int is_last, mk_runs *runs)
+{
+    if (!ctx || !runs) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    u64 *cc = nullptr, *cp = nullptr, n_cand = 0, nl = 0;
+    CKR(mk_stream_fastq(ctx, (const uint8_t *)d_text, nbytes, pos_base, line_base, false, &cc, &cp, &n_cand, &nl));
+    long long keep_below = LLONG_MAX;
+    if (is_last && nbytes) {
+        CKR(mk_tail_cut(ctx, (const uint8_t *)d_text, nbytes, &keep_below));
+        if (keep_below >= 0) keep_below += (long long)pos_base; else keep_below = (long long)pos_base;
+    }
+    u64 *it_key, *it_pos, n_items;
+    u32 *it_cnt;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    CKR(mk_reduce_candidates(ctx, cc, cp, n_cand, keep_below, nullptr, 1, ctx->info.code_bits, &it_key, &it_cnt, &it_pos,
+                             &n_items));
+    int rc = runs_sorted_by_code(ctx, it_key, it_cnt, it_pos, n_items, runs);
+    cudaEventRecord(ctx->ev3, ctx->stream);
+    cudaEventSynchronize(ctx->ev3);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.reduce_ms += ms;
+    return rc;
+}
+
+extern "C" int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
+                                    const uint32_t *d_count, uint64_t n, mk_runs *merged)
+{
+    if (!ctx || !merged) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    u64 *it_key, *it_pos, n_items;
+    u32 *it_cnt;
+    CKR(accumulate(ctx, (const u64 *)d_code, (const u64 *)d_firstpos, d_count, n, LLONG_MAX, nullptr, 1,
+                   ctx->info.code_bits, false, &it_key, &it_cnt, &it_pos, &n_items));
+    return runs_sorted_by_code(ctx, it_key, it_cnt, it_pos, n_items, merged);
+}
+
+extern "C" int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
+                                       const uint32_t *d_count, uint64_t n, mk_sketch *out)
+{
+    if (!ctx || !out) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    u64 *it_key, *it_pos, n_items;
+    u32 *it_cnt;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    CKR(accumulate(ctx, (const u64 *)d_code, (const u64 *)d_firstpos, d_count, n, LLONG_MAX, nullptr, 1,
+                   ctx->info.code_bits, false, &it_key, &it_cnt, &it_pos, &n_items));
+    int rc = mk_order_and_emit(ctx, it_key, it_cnt, it_pos, n_items, 1, true, false, out);
+    cudaEventRecord(ctx->ev3, ctx->stream);
+    cudaEventSynchronize(ctx->ev3);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.reduce_ms += ms;
+    return rc;
+}

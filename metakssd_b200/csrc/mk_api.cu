@@ -137,11 +137,19 @@ extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int 
     else bm_words = 1u << (K.mw - 5);
     if (bm_words < 4) bm_words = 4;
     std::vector<u32> bitmap(bm_words, 0);
+    // mw >= 22: two-hash Bloom filter in 2^20 bits (first hash: window bits 2..21, second hash:
+    // bits {0,1,6..23}); mw <= 20: exact bitmap.  Mirrors probe_block()/second_hash_hit().
     auto set_bit = [&](u64 q) {
         u32 word, bit;
-        if (K.mw >= 22) { word = (u32)(q >> 2) & 0x7FFFu; bit = (u32)(q >> 17) & 31u; }
-        else { word = (u32)(q & ((1ull << (K.mw - 5)) - 1)); bit = (u32)(q >> (K.mw - 5)) & 31u; }
-        bitmap[word] |= 1u << (31 - bit);
+        if (K.mw >= 22) {
+            word = (u32)(q >> 2) & 0x7FFFu; bit = (u32)(q >> 17) & 31u;
+            bitmap[word] |= 1u << (31 - bit);
+            word = (u32)(q >> 6) & 0x7FFFu; bit = ((u32)(q >> 21) & 7u) | (((u32)q & 3u) << 3);
+            bitmap[word] |= 1u << (31 - bit);
+        } else {
+            word = (u32)(q & ((1ull << (K.mw - 5)) - 1)); bit = (u32)(q >> (K.mw - 5)) & 31u;
+            bitmap[word] |= 1u << (31 - bit);
+        }
     };
     for (u64 d = 0; d < ndim; d++) {
         int32_t pf = shuf_perm[d];

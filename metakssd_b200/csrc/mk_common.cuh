@@ -13,10 +13,9 @@ typedef unsigned long long u64;
 typedef unsigned int u32;
 
 #define MK_HALO 32            // bytes of left context staged in front of every text tile
-#define MK_MAX_TILE 32768     // tile-proper bytes (multiple of 64)
+#define MK_MAX_TILE 24576     // tile-proper bytes (multiple of 64); three stages fit beside the bitmap
 #define MK_STREAM_THREADS 512
-#define MK_MAXL 1024          // sequence lines handled per marker window
-#define MK_HITCAP 2048
+#define MK_HITCAP 1024        // first-level bitmap hits queued per tile
 
 // ---- sketch parameters mirrored on the device (values of iseq2comem.c:54-86) -------------------
 struct KParams {

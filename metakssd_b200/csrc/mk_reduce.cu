@@ -181,6 +181,12 @@ k_gather_ranked(const u64 *__restrict__ perm, u64 n, const u64 *__restrict__ it_
     }
 }
 
+__global__ void __launch_bounds__(256) k_count_files(const u64 *__restrict__ it_key, u64 n, int code_bits, u32 *__restrict__ fc)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&fc[it_key[i] >> code_bits], 1u);
+}
+
 __device__ __forceinline__ u32 probe_slot(u64 code, u64 i, u64 hs)
 {
     // global_basic.h:282-284 — 64-bit arithmetic
@@ -197,6 +203,7 @@ k_slot_assign(const u64 *__restrict__ r_key, u64 n, int code_bits, u64 hs, u64 *
     u32 carry = (u32)r;
     u64 i = 0;
     for (;;) {
+        if (i >= hs) return;                 // cannot happen below hashlimit; never spin on a full table
         u64 key = r_key[carry];
         u64 file = key >> code_bits, code = key & cmask;
         u32 slot = probe_slot(code, i, hs);
@@ -272,8 +279,30 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
     }
     if (n == 0) return MK_OK;
     if (n >= 0xFFFFFFF0ull) return MK_ERR_UNSUPPORTED;
-
     const u64 nb = (n + 255) / 256;
+    // The reference aborts as soon as a table holds more than hashlimit codes (iseq2comem.c:708,
+    // :303); check before reconstructing slots (a table with more codes than slots has no layout).
+    {
+        bool crowded = false;
+        if (n_files == 1) crowded = n > I.hashlimit;
+        else if (n > I.hashlimit) {
+            u32 *fc;
+            CKR(mk_scratch(ctx, SB_SEG_COUNTS, (size_t)n_files * 2 + 2, &fc));
+            CK(cudaMemsetAsync(fc, 0, (size_t)n_files * 4, ctx->stream));
+            k_count_files<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_it_key, n, code_bits, fc);
+            LAUNCH_COUNT(ctx);
+            std::vector<u32> h((size_t)n_files);
+            CK(cudaMemcpyAsync(h.data(), fc, (size_t)n_files * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (int f = 0; f < n_files; f++) crowded |= h[f] > I.hashlimit;
+        }
+        if (crowded) {
+            snprintf(ctx->err, sizeof(ctx->err),
+                     "the context space is too crowd, try rerun the program using -k%d", I.k + 1);
+            return MK_ERR_CROWDED;
+        }
+    }
+
     u64 *k0, *v0, *k1, *v1;
     CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n, &k0));
     CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n, &v0));

@@ -31,6 +31,7 @@ struct StreamArgs {
     const u32 *bitmap;
     u32 bitmap_bytes;
     const u64 *ptab;
+    u32 two_hash;           // 1: the bitmap is a two-hash Bloom filter (inner window of 22+ bits)
     u64 *cand_code;
     u64 *cand_pos;
     u64 *cand_count;
@@ -40,7 +41,7 @@ struct StreamArgs {
     KParams kp;
 };
 
-#define TBUF_STRIDE (MK_HALO + MK_MAX_TILE + 96) // keeps both buffers 128-byte aligned
+#define TBUF_STRIDE (MK_HALO + MK_MAX_TILE + 96) // keeps the stage buffers 128-byte aligned
 #define FLAG_LONG_LINE 2u
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
@@ -206,15 +207,15 @@ __device__ __forceinline__ u32 pack16(uint4 v)
 
 // Probe the 32 k-mer end positions of one aligned 32-byte block against the bitmap.
 // blk = shared-memory address of the block's first byte.  Bit j of the result = position j hit.
+// A[0..2] receive the packed bases, position j's inner window starting at bit 2j.
 template <int ROTOFF, u32 WORDMASK, int PREW>
-__device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, int shift_s)
+__device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, int shift_s, u32 (&A)[4])
 {
     u32 W[PREW + 3];
     const uint4 *q = reinterpret_cast<const uint4 *>(blk - 16 * PREW);
 #pragma unroll
     for (int i = 0; i < PREW + 2; i++) W[i] = pack16(q[i]);
     W[PREW + 2] = 0;
-    u32 A[4];
     A[0] = __funnelshift_r(W[0], W[1], shift_s);
     A[1] = __funnelshift_r(W[1], W[2], shift_s);
     A[2] = __funnelshift_r(W[2], W[3], shift_s);
@@ -232,7 +233,75 @@ __device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, in
     return __brev(hits);
 }
 
+// Second hash of the two-hash Bloom filter (inner windows of 22 bits or more): uses window bits
+// {0,1} and {6..23}, i.e. includes the four bits the first hash ignores.  Must mirror set_bit() in
+// mk_api.cu.
+__device__ __forceinline__ bool second_hash_hit(const u32 (&A)[4], u32 j, const u32 *bm)
+{
+    u32 lo = j < 16 ? A[0] : A[1];
+    u32 hi = j < 16 ? A[1] : A[2];
+    u32 v = __funnelshift_r(lo, hi, (2 * j) & 31);
+    u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + ((v >> 4) & 0x1FFFCu));
+    u32 bit = ((v >> 21) & 7u) | ((v & 3u) << 3);
+    return (word >> (31u - bit)) & 1u;
+}
+
+__device__ __forceinline__ void emit_candidate(const StreamArgs &A, u64 code, u64 pos)
+{
+    u64 idx = atomicAdd((unsigned long long *)A.cand_count, 1ull);
+    if (idx < A.cand_cap) {
+        A.cand_code[idx] = code;
+        A.cand_pos[idx] = pos;
+    }
+}
+
+#define MAXBLK (MK_MAX_TILE / 32)
+#define MAXCHUNK (MK_MAX_TILE / 2048)   // scan chunks: one warp pass = 32 lanes x 64 bytes
+#define NWARPS (MK_STREAM_THREADS / 32)
+#define WHITS 32                         // verified-later hits buffered per warp
+
+// inclusive prefix XOR over the 32 bits of x
+__device__ __forceinline__ u32 prefix_xor(u32 x)
+{
+    x ^= x << 1; x ^= x << 2; x ^= x << 4; x ^= x << 8; x ^= x << 16;
+    return x;
+}
+
 // ---- the kernel --------------------------------------------------------------------------------
+// Per CTA three tiles (cur, next, next-next) are resident in shared memory.  One iteration has a
+// single block-wide barrier; after it every warp pulls work units until none are left:
+//
+//   P  probe units of `cur`  : 32 items (aligned 32-byte blocks holding sequence bytes) per pull.
+//                              Hits that pass both Bloom hashes are queued; the LAST warp to leave
+//                              the probe loop verifies the queue exactly (22 valid ACGT bytes,
+//                              canonical strand, exact pass table) and then recycles the stage of
+//                              `cur` (new ticket, TMA issued).
+//   M  mask units of `next`  : per 32-byte block, newline mask + line number -> mask of sequence
+//                              bytes (branch-free prefix-parity arithmetic); blocks with any
+//                              sequence byte are appended to next's item list.  Needs the line
+//                              number of `next`, which warp 0 resolves first (decoupled look-back;
+//                              every predecessor published its count at least one iteration ago).
+//   S  scan units of `next-next`: 2 KB chunks scanned for '\n' (mask per block, count per chunk);
+//                              the warp completing the last chunk publishes the tile's count.
+struct StreamSmem {
+    u32 nlm[3][MAXBLK];          // newline mask of each 32-byte block
+    uint16_t exw[3][MAXBLK];     // '\n' bytes before the block inside its chunk
+    u32 ctot[3][MAXCHUNK];       // '\n' bytes per chunk
+    u32 cpre[3][MAXCHUNK];       // '\n' bytes before each chunk inside the tile
+    u32 posmask[2][MAXBLK];      // double buffered: tile being probed / tile being masked
+    uint16_t items[2][MAXBLK];
+    uint16_t hitq[MK_HITCAP];
+    u64 bar[3];
+    u64 P[3];                    // '\n' bytes before each staged tile (line number of its first byte)
+    u32 tile[3];                 // ticket held by each stage
+    u32 tot[3];                  // '\n' bytes in each staged tile
+    u32 scur[3];                 // scan-chunk cursor per stage
+    u32 sdone[3];                // scanned chunks per stage
+    u32 n_items[2];              // items per buffer
+    u32 icur, bdone, mcur, nhits;
+    volatile u32 resolved;       // iteration stamp: line number of `next` is available
+};
+
 template <int ROTOFF, u32 WORDMASK, int PREW, bool RAW>
 __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_constant__ StreamArgs A)
 {
@@ -242,224 +311,299 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
     const u32 bm_bytes = (A.bitmap_bytes + 127u) & ~127u;
     u32 *bm = reinterpret_cast<u32 *>(smem);
     uint8_t *tbuf = smem + bm_bytes;
-    uint8_t *p = tbuf + 2 * TBUF_STRIDE;
-    uint16_t *starts = reinterpret_cast<uint16_t *>(p); p += MK_MAXL * 2;
-    uint16_t *ends = reinterpret_cast<uint16_t *>(p);   p += MK_MAXL * 2;
-    u32 *posmask = reinterpret_cast<u32 *>(p);          p += (MK_MAX_TILE / 32) * 4;
-    uint16_t *items = reinterpret_cast<uint16_t *>(p);  p += (MK_MAX_TILE / 32) * 2;
-    uint16_t *hitq = reinterpret_cast<uint16_t *>(p);   p += MK_HITCAP * 2;
-    u32 *ws = reinterpret_cast<u32 *>(p);               p += 20 * 4;
-    u32 *ws2 = reinterpret_cast<u32 *>(p);              p += 20 * 4;
-    u64 *bar = reinterpret_cast<u64 *>(p);              p += 16;
-    u64 *s_P = reinterpret_cast<u64 *>(p);              p += 8;
-    u32 *s_tile = reinterpret_cast<u32 *>(p);           p += 8;
-    u32 *s_nhits = reinterpret_cast<u32 *>(p);          p += 8;
+    StreamSmem &S = *reinterpret_cast<StreamSmem *>(tbuf + 3 * TBUF_STRIDE);
 
-    // bitmap -> shared memory
-    {
+    {   // bitmap -> shared memory
         const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
         uint4 *dst = reinterpret_cast<uint4 *>(bm);
         for (u32 i = tid; i < A.bitmap_bytes / 16; i += MK_STREAM_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        mbar_init(&bar[0], 1);
-        mbar_init(&bar[1], 1);
+        for (int s = 0; s < 3; s++) { mbar_init(&S.bar[s], 1); S.scur[s] = 0; S.sdone[s] = 0; S.tot[s] = 0; S.P[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.n_items[0] = 0; S.n_items[1] = 0; S.icur = 0; S.bdone = 0; S.mcur = 0; S.nhits = 0; S.resolved = 0;
     }
     __syncthreads();
 
     const u32 TB = A.tile_bytes;
-    auto issue_load = [&](int stage, u32 t) {
-        u64 T = (u64)t * TB;
-        u64 rem = A.nbytes - T;
-        u32 tb = rem < TB ? (u32)rem : TB;
+    const u32 NBLK = TB / 32;
+    const u32 NCHUNK = (TB + 2047u) / 2048u;
+    const u32 NMUNIT = (NBLK + 31u) / 32u;
+    auto tile_len = [&](u32 t) -> u32 {
+        u64 rem = A.nbytes - (u64)t * TB;
+        return rem < TB ? (u32)rem : TB;
+    };
+    auto claim_and_load = [&](int stage) {   // one thread
+        u32 t = atomicAdd(A.tile_counter, 1u);
+        S.tile[stage] = t;
+        S.scur[stage] = 0;
+        S.sdone[stage] = 0;
+        if (t >= A.n_tiles) return;
+        u32 tb = tile_len(t);
         uint8_t *dst = tbuf + stage * TBUF_STRIDE;
-        const uint8_t *src = A.text + T;
+        const uint8_t *src = A.text + (u64)t * TB;
         u32 bytes = tb;
         if (t > 0) { src -= MK_HALO; bytes += MK_HALO; } else { dst += MK_HALO; }
         bytes = (bytes + 15u) & ~15u;
-        fence_proxy_async(); // order earlier generic-proxy writes to this buffer before the bulk copy
-        mbar_expect_tx(&bar[stage], bytes);
-        tma_load_1d(dst, src, bytes, &bar[stage]);
+        fence_proxy_async();
+        mbar_expect_tx(&S.bar[stage], bytes);
+        tma_load_1d(dst, src, bytes, &S.bar[stage]);
     };
-
-    if (tid == 0) {
-        u32 t = atomicAdd(A.tile_counter, 1u);
-        s_tile[0] = t;
-        if (t < A.n_tiles) issue_load(0, t);
-    }
-    __syncthreads();
-    u32 cur = s_tile[0];
-    int stage = 0;
-    u32 parity0 = 0, parity1 = 0;
-
-    while (cur < A.n_tiles) {
-        if (tid == 0) {
-            u32 t = atomicAdd(A.tile_counter, 1u);
-            s_tile[stage ^ 1] = t;
-            if (t < A.n_tiles) issue_load(stage ^ 1, t);
-            *s_nhits = 0;
-        }
-        if (stage == 0) { mbar_wait(&bar[0], parity0); parity0 ^= 1; }
-        else            { mbar_wait(&bar[1], parity1); parity1 ^= 1; }
-
-        uint8_t *tx = tbuf + stage * TBUF_STRIDE; // tx[0..HALO) = left context, tile bytes from tx+HALO
-        const u64 T = (u64)cur * TB;
-        const u64 rem = A.nbytes - T;
-        const u32 tb = rem < TB ? (u32)rem : TB;
-        if (cur == 0 && tid < MK_HALO / 4) reinterpret_cast<u32 *>(tx)[tid] = 0; // no text before the file
-        if (tb < TB) { // last tile: blank everything past the end of the text
-            for (u32 i = MK_HALO + tb + tid; i < MK_HALO + TB; i += MK_STREAM_THREADS) tx[i] = 0;
-            fence_proxy_async();
-        }
-        // zero posmask (2 words per thread)
-        posmask[2 * tid] = 0;
-        posmask[2 * tid + 1] = 0;
-        __syncthreads();
-
-        u32 n_items = 0;
-        if (RAW) {
-            // every byte is a base-stream byte: all blocks below tb are items
-            u32 nblk = (tb + 31) >> 5;
-            for (u32 b = tid; b < nblk; b += MK_STREAM_THREADS) {
-                items[b] = (uint16_t)b;
-                u32 left = tb - 32 * b;
-                posmask[b] = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+    // S units: scan the tile in `stage` (chunks pulled dynamically by whole warps).
+    auto scan_units = [&](int stage, u32 use_parity) {
+        const u32 t = S.tile[stage];
+        if (t >= A.n_tiles) return;                        // uniform per CTA
+        uint8_t *tx = tbuf + stage * TBUF_STRIDE;
+        const u32 tb = tile_len(t);
+        bool waited = false;
+        for (;;) {
+            u32 c = 0;
+            if (lane == 0) c = atomicAdd(&S.scur[stage], 1u);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= NCHUNK) break;
+            if (!waited) { mbar_wait(&S.bar[stage], use_parity); waited = true; }
+            const u32 off = c * 2048u + lane * 64u;        // my 64 bytes (two blocks)
+            // blank what lies outside the text so that stale bytes can never look like sequence
+            if (t == 0 && c == 0 && lane < MK_HALO / 4) reinterpret_cast<u32 *>(tx)[lane] = 0;
+            if (off + 64u > tb && off < TB) {
+                u32 from = off > tb ? off : tb;
+                for (u32 i = from; i < off + 64u; i++) tx[MK_HALO + i] = 0;
             }
-            n_items = nblk;
-            __syncthreads();
-        } else {
-            // ---- A1: newline mask of my 64 bytes ----
-            u64 nl = 0;
-            const u32 off = tid * 64;
-            if (off < TB) {
+            u32 m0 = 0, m1 = 0;
+            if (!RAW && off < TB) {
                 const uint4 *q = reinterpret_cast<const uint4 *>(tx + MK_HALO + off);
+                u32 w[16];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    uint4 v = q[c];
-                    u32 w4[4] = {v.x, v.y, v.z, v.w};
+                for (int k4 = 0; k4 < 4; k4++) { uint4 v = q[k4]; w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w; }
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        u32 y = w4[j] ^ 0x0A0A0A0Au;
-                        u32 t7 = (y & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                        u32 f = ~(t7 | y) & 0x80808080u;            // 0x80 where the byte is '\n'
-                        u32 nib = __umulhi(f, 0x02040810u) & 0xFu;   // gather bits 7,15,23,31
-                        nl |= (u64)nib << (16 * c + 4 * j);
-                    }
+                for (int j = 0; j < 16; j++) {
+                    // exact "byte == 0x0A": bit 7 of t7 is set iff the low 7 bits of (byte ^ 0x0A) are non-zero
+                    u32 t7 = ((w[j] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                    u32 f = ~(t7 | w[j]) & 0x80808080u;
+                    u32 nib = __umulhi(f, 0x02040810u);   // bits 7,15,23,31 -> bits 0..3 (junk above)
+                    if (j < 8) m0 = __funnelshift_r(m0, nib, 4);
+                    else       m1 = __funnelshift_r(m1, nib, 4);
                 }
             }
-            const u32 cnt = __popcll(nl);
-            u32 total;
-            const u32 excl = block_excl_scan_512(cnt, ws, &total);
-            if (wid == 0) {
-                u64 e = tile_lookback(A.tile_desc, cur, (u64)total);
+            if (!RAW) {
+                const u32 c0 = __popc(m0), cnt = c0 + __popc(m1);
+                u32 incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (u32)o) incl += v;
+                }
+                const u32 b0 = c * 64u + 2u * lane;
+                if (b0 < NBLK) {
+                    S.nlm[stage][b0] = m0;
+                    S.exw[stage][b0] = (uint16_t)(incl - cnt);
+                }
+                if (b0 + 1 < NBLK) {
+                    S.nlm[stage][b0 + 1] = m1;
+                    S.exw[stage][b0 + 1] = (uint16_t)(incl - cnt + c0);
+                }
+                if (lane == 31) S.ctot[stage][c] = incl;
+            }
+            fence_proxy_async();
+            __threadfence_block();
+            __syncwarp();
+            u32 fin = 0;
+            if (lane == 0) fin = atomicAdd(&S.sdone[stage], 1u);
+            fin = __shfl_sync(0xffffffffu, fin, 0);
+            if (fin == NCHUNK - 1 && !RAW) {               // this warp completed the tile's scan
+                __threadfence_block();
+                u32 v = lane < NCHUNK ? S.ctot[stage][lane] : 0;
+                u32 incl = v;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (u32)o) incl += x;
+                }
+                if (lane < NCHUNK) S.cpre[stage][lane] = incl - v;
+                u32 total = __shfl_sync(0xffffffffu, incl, 15);   // NCHUNK <= 12 lanes carry values
                 if (lane == 0) {
-                    *s_P = A.line_base + e;
-                    if (cur == A.n_tiles - 1) *A.total_newlines = A.line_base + e + total;
+                    S.tot[stage] = total;
+                    st_volatile_u64(&A.tile_desc[t], ((t == 0 ? 2ull : 1ull) << 62) | (u64)total);
                     if (total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
                 }
             }
-            __syncthreads();
-            const u64 P = *s_P;                     // '\n' bytes before the tile == line index of its first byte
-            const u64 q0 = (P + 2) >> 2;            // record number of the first sequence line touching the tile
-            const u32 in_seq = ((P & 3) == 1);
-            const u32 n_seq = (u32)(((P + total + 3) >> 2) - ((P + 3) >> 2)) + in_seq;
-
-            // ---- markers -> posmask, in windows of MK_MAXL sequence lines ----
-            for (u32 w0 = 0; w0 < n_seq; w0 += MK_MAXL) {
-                const u32 wn = (n_seq - w0) < MK_MAXL ? (n_seq - w0) : MK_MAXL;
-                for (u32 i = tid; i < wn; i += MK_STREAM_THREADS) {
-                    starts[i] = (uint16_t)((w0 == 0 && i == 0 && in_seq) ? 0 : tb);
-                    ends[i] = (uint16_t)tb;
-                }
-                __syncthreads();
-                if (cnt) {
-                    u64 m = nl;
-                    u64 line = P + excl;            // index of the line my first newline terminates
-                    while (m) {
-                        u32 bit = __ffsll((long long)m) - 1;
-                        m &= m - 1;
-                        u32 pos = off + bit;
-                        u32 ph = (u32)line & 3u;
-                        if (ph <= 1) {
-                            u64 ord = (line >> 2) - q0;
-                            if (ord >= w0 && ord < (u64)w0 + wn) {
-                                if (ph == 0) starts[ord - w0] = (uint16_t)(pos + 1 > tb ? tb : pos + 1);
-                                else         ends[ord - w0] = (uint16_t)pos;
-                            }
-                        }
-                        line++;
-                    }
-                }
-                __syncthreads();
-                for (u32 i = tid; i < wn; i += MK_STREAM_THREADS) {
-                    u32 s = starts[i], e = ends[i];
-                    if (e > s) {
-                        u32 b0 = s >> 5, b1 = (e - 1) >> 5;
-                        for (u32 b = b0; b <= b1; b++) {
-                            u32 msk = 0xffffffffu;
-                            if (b == b0) msk &= 0xffffffffu << (s & 31);
-                            if (b == b1) msk &= 0xffffffffu >> (31 - ((e - 1) & 31));
-                            atomicOr(&posmask[b], msk);
-                        }
-                    }
-                }
-                __syncthreads();
+        }
+    };
+    // exclusive prefix of tile t's newline count (warp 0, all lanes); publishes the inclusive value
+    auto resolve_tile = [&](u32 t, u32 total) -> u64 {
+        const u64 VMASK = (1ull << 62) - 1;
+        if (t == 0) return 0;
+        u64 excl = 0;
+        long long look = (long long)t - 1;
+        for (;;) {
+            long long idx = look - (long long)lane;
+            u64 d;
+            do {
+                d = idx >= 0 ? ld_volatile_u64(&A.tile_desc[idx]) : (2ull << 62);
+            } while (__any_sync(0xffffffffu, (d >> 62) == 0));
+            u32 m2 = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+            u64 val = d & VMASK;
+            if (m2) {
+                u32 first = __ffs(m2) - 1;
+                excl += warp_sum_u64(lane <= first ? val : 0);
+                break;
             }
-            // ---- compact blocks that hold sequence bytes into the item list ----
-            const u32 a0 = posmask[2 * tid] != 0, a1 = posmask[2 * tid + 1] != 0;
-            u32 tot2;
-            u32 ioff = block_excl_scan_512(a0 + a1, ws2, &tot2);
-            if (a0) items[ioff++] = (uint16_t)(2 * tid);
-            if (a1) items[ioff] = (uint16_t)(2 * tid + 1);
-            n_items = tot2;
-            __syncthreads();
+            excl += warp_sum_u64(val);
+            look -= 32;
+        }
+        if (lane == 0) st_volatile_u64(&A.tile_desc[t], (2ull << 62) | ((excl + total) & VMASK));
+        return excl;
+    };
+    // M units: sequence-byte masks + item list of the tile in `stage`, into buffer `buf`
+    auto mask_units = [&](int stage, int buf) {
+        const u32 t = S.tile[stage];
+        if (t >= A.n_tiles) return;
+        const u32 tb = tile_len(t);
+        const u32 P = RAW ? 0u : (u32)S.P[stage];
+        for (;;) {
+            u32 u = 0;
+            if (lane == 0) u = atomicAdd(&S.mcur, 1u);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= NMUNIT) break;
+            const u32 b = u * 32u + lane;
+            u32 pm = 0;
+            if (b < NBLK) {
+                if (RAW) {
+                    u32 lo = 32 * b;
+                    pm = lo >= tb ? 0u : (tb - lo >= 32 ? 0xffffffffu : ((1u << (tb - lo)) - 1u));
+                } else {
+                    // line(i) = P + '\n' before the block + '\n' among bytes < i of the block; a byte is a
+                    // sequence byte iff line(i) % 4 == 1 and it is not the '\n' itself.  The two low bits
+                    // of the running count are prefix parities of the newline mask.
+                    const u32 nl = S.nlm[stage][b];
+                    const u32 s0 = (P + S.cpre[stage][b >> 6] + S.exw[stage][b]) & 3u;
+                    const u32 tgt = (1u - s0) & 3u;              // count % 4 that puts a byte on phase 1
+                    u32 p0 = 0, p1 = 0;
+                    if (nl) {
+                        p0 = prefix_xor(nl << 1);                // parity of '\n' strictly before each byte
+                        p1 = prefix_xor((nl & p0) << 1);         // carries out of bit 0
+                    }
+                    pm = (p0 ^ ((tgt & 1u) ? 0u : ~0u)) & (p1 ^ ((tgt & 2u) ? 0u : ~0u)) & ~nl;
+                }
+                S.posmask[buf][b] = pm;
+            }
+            const bool act = pm != 0;
+            const u32 m = __ballot_sync(0xffffffffu, act);
+            u32 base = 0;
+            if (lane == 0 && m) base = atomicAdd(&S.n_items[buf], (u32)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (act) S.items[buf][base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
+        }
+    };
+
+    // ---- prologue: three tickets; scan the first two; resolve + mask the first ----------------
+    if (tid == 0)
+        for (int s = 0; s < 3; s++) claim_and_load(s);
+    __syncthreads();
+    u32 uses0 = 0, uses1 = 0, uses2 = 0;       // completed uses of each stage's mbarrier (parity)
+    scan_units(0, 0); uses0 = 1;
+    scan_units(1, 0); uses1 = 1;
+    __syncthreads();
+    if (!RAW && wid == 0 && S.tile[0] < A.n_tiles) {
+        u64 e = resolve_tile(S.tile[0], S.tot[0]);
+        if (lane == 0) {
+            S.P[0] = A.line_base + e;
+            if (S.tile[0] == A.n_tiles - 1) *A.total_newlines = A.line_base + e + S.tot[0];
+        }
+    }
+    __syncthreads();
+    mask_units(0, 0);
+
+    int stage = 0, buf = 0;
+    u32 iter = 0;
+    for (;;) {
+        __syncthreads();                                   // the only block-wide barrier per tile
+        const u32 cur = S.tile[stage];
+        if (cur >= A.n_tiles) break;
+        iter++;
+        const int st1 = stage == 2 ? 0 : stage + 1;       // next tile
+        const int st2 = st1 == 2 ? 0 : st1 + 1;           // tile after next
+        uint8_t *tx = tbuf + stage * TBUF_STRIDE;
+        const u64 T = (u64)cur * TB;
+        const u32 n_items = S.n_items[buf];
+        if (tid == 0) S.mcur = 0;                          // nobody pulls M units before `resolved` is stamped
+
+        // warp 0: line number of the next tile, then stamp it
+        if (wid == 0) {
+            const u32 nt = S.tile[st1];
+            if (!RAW && nt < A.n_tiles) {
+                u64 e = resolve_tile(nt, S.tot[st1]);
+                if (lane == 0) {
+                    S.P[st1] = A.line_base + e;
+                    if (nt == A.n_tiles - 1) *A.total_newlines = A.line_base + e + S.tot[st1];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); S.resolved = iter; }
         }
 
-        // ---- B: probe ----
-        for (u32 it = tid; it < n_items; it += MK_STREAM_THREADS) {
-            const u32 b = items[it];
-            u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s);
-            hits &= posmask[b];
-            while (hits) {
-                u32 j = __ffs(hits) - 1;
-                hits &= hits - 1;
-                u32 slot = atomicAdd(s_nhits, 1u);
-                u32 pos = 32 * b + j;
-                if (slot < MK_HITCAP) {
-                    hitq[slot] = (uint16_t)pos;
-                } else { // queue full: verify in place
+        // ---- P units ---------------------------------------------------------------------------
+        for (;;) {
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(&S.icur, 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= n_items) break;
+            const u32 it = base + lane;
+            if (it < n_items) {
+                const u32 b = S.items[buf][it];
+                u32 Aw[4];
+                u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
+                hits &= S.posmask[buf][b];
+                while (hits) {
+                    u32 j = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
+                    u32 pos = 32 * b + j;
+                    u32 slot = atomicAdd(&S.nhits, 1u);
+                    if (slot < MK_HITCAP) {
+                        S.hitq[slot] = (uint16_t)pos;
+                    } else {                               // queue full: finish this hit in place
+                        u64 code;
+                        if (verify_kmer(tx + MK_HALO + pos, A.kp, A.ptab, &code))
+                            emit_candidate(A, code, A.pos_base + T + pos);
+                    }
+                }
+            }
+        }
+        {   // last warp out: verify the queued hits, then recycle the stage of `cur`
+            u32 d = 0;
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); d = atomicAdd(&S.bdone, 1u); }
+            d = __shfl_sync(0xffffffffu, d, 0);
+            if (d == NWARPS - 1) {
+                __threadfence_block();
+                u32 nh = S.nhits;
+                if (nh > MK_HITCAP) nh = MK_HITCAP;
+                for (u32 h = lane; h < nh; h += 32) {
+                    u32 pos = S.hitq[h];
                     u64 code;
-                    if (verify_kmer(tx + MK_HALO + pos, A.kp, A.ptab, &code)) {
-                        u64 idx = atomicAdd((unsigned long long *)A.cand_count, 1ull);
-                        if (idx < A.cand_cap) {
-                            A.cand_code[idx] = code;
-                            A.cand_pos[idx] = A.pos_base + T + pos;
-                        }
-                    }
+                    if (verify_kmer(tx + MK_HALO + pos, A.kp, A.ptab, &code))
+                        emit_candidate(A, code, A.pos_base + T + pos);
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    S.n_items[buf] = 0; S.icur = 0; S.bdone = 0; S.nhits = 0;
+                    claim_and_load(stage);
                 }
             }
         }
-        __syncthreads();
-        // ---- C: exact verification of queued hits ----
+        // ---- M units of the next tile (after its line number is known) -------------------------
+        while (S.resolved != iter) {}
+        __threadfence_block();
+        mask_units(st1, buf ^ 1);
+        // ---- S units of the tile two ahead -----------------------------------------------------
         {
-            u32 nh = *s_nhits;
-            if (nh > MK_HITCAP) nh = MK_HITCAP;
-            for (u32 h = tid; h < nh; h += MK_STREAM_THREADS) {
-                u32 pos = hitq[h];
-                u64 code;
-                if (verify_kmer(tx + MK_HALO + pos, A.kp, A.ptab, &code)) {
-                    u64 idx = atomicAdd((unsigned long long *)A.cand_count, 1ull);
-                    if (idx < A.cand_cap) {
-                        A.cand_code[idx] = code;
-                        A.cand_pos[idx] = A.pos_base + T + pos;
-                    }
-                }
-            }
+            u32 par = st2 == 0 ? (uses0 & 1u) : (st2 == 1 ? (uses1 & 1u) : (uses2 & 1u));
+            scan_units(st2, par);
+            if (st2 == 0) uses0++; else if (st2 == 1) uses1++; else uses2++;
         }
-        __syncthreads();
-        cur = s_tile[stage ^ 1];
-        stage ^= 1;
+        stage = st1;
+        buf ^= 1;
     }
 }
 
@@ -556,11 +700,8 @@ static stream_kernel_t pick_kernel(const KParams &kp, bool raw)
 static size_t stream_smem_bytes(u32 bitmap_bytes)
 {
     size_t s = (bitmap_bytes + 127u) & ~127u;
-    s += 2 * TBUF_STRIDE;
-    s += MK_MAXL * 2 * 2;
-    s += (MK_MAX_TILE / 32) * 4 + (MK_MAX_TILE / 32) * 2;
-    s += MK_HITCAP * 2;
-    s += 20 * 4 * 2 + 16 + 8 + 8 + 8;
+    s += 3 * TBUF_STRIDE;
+    s += sizeof(StreamSmem);
     return s + 64;
 }
 
@@ -580,10 +721,14 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         snprintf(ctx->err, sizeof(ctx->err), "unsupported inner substring width subk=%d", kp.subk);
         return MK_ERR_UNSUPPORTED;
     }
-    u32 tile_bytes = raw_mode ? 16384u : 32768u;
+    // tile-proper bytes: a multiple of 64 (two 32-byte probe blocks per scanning thread)
+    u32 tile_bytes = raw_mode ? 16384u : (u32)MK_MAX_TILE;
     if (const char *e = getenv(raw_mode ? "MK_RAW_TILE_BYTES" : "MK_TILE_BYTES")) {
         u32 v = (u32)atoi(e);
-        if (v >= 64 && v <= MK_MAX_TILE) tile_bytes = v & ~63u;
+        v &= ~63u;
+        if (v < 64u) v = 64u;
+        if (v > MK_MAX_TILE) v = MK_MAX_TILE;
+        tile_bytes = v;
     }
     u64 n_tiles64 = (nbytes + tile_bytes - 1) / tile_bytes;
     if (n_tiles64 > 0x7FFFFFFFull) return MK_ERR_UNSUPPORTED;
@@ -609,7 +754,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         a.tile_bytes = tile_bytes; a.n_tiles = n_tiles; a.tile_desc = desc;
         a.cand_count = counters + 0; a.total_newlines = counters + 1;
         a.tile_counter = (u32 *)(counters + 2); a.flags = (u32 *)(counters + 2) + 1;
-        a.bitmap = ctx->d_bitmap; a.bitmap_bytes = ctx->bitmap_words * 4; a.ptab = ctx->d_ptab;
+        a.bitmap = ctx->d_bitmap; a.bitmap_bytes = ctx->bitmap_words * 4; a.ptab = ctx->d_ptab; a.two_hash = ctx->kp.mw >= 22 ? 1u : 0u;
         a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp;
         u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));

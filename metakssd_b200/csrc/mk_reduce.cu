@@ -52,6 +52,7 @@ k_acc_insert(const u64 *__restrict__ cand_code, const u64 *__restrict__ cand_pos
     if (i >= n) return;
     u64 pos = cand_pos[i];
     if ((long long)pos >= keep_below) return;
+    if (cand_code[i] == EMPTY64) return;    // hit rejected by k_verify
     u64 file = 0;
     if (file_off) {
         int lo = 0, hi = n_files - 1; // largest f with file_off[f] <= pos

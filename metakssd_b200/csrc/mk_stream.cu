@@ -246,13 +246,12 @@ __device__ __forceinline__ bool second_hash_hit(const u32 (&A)[4], u32 j, const 
     return (word >> (31u - bit)) & 1u;
 }
 
-__device__ __forceinline__ void emit_candidate(const StreamArgs &A, u64 code, u64 pos)
+// A position that passed the shared-memory filter: appended to the global hit list; k_verify turns
+// it into a (code, position) candidate or drops it.
+__device__ __forceinline__ void emit_hit(const StreamArgs &A, u64 pos)
 {
     u64 idx = atomicAdd((unsigned long long *)A.cand_count, 1ull);
-    if (idx < A.cand_cap) {
-        A.cand_code[idx] = code;
-        A.cand_pos[idx] = pos;
-    }
+    if (idx < A.cand_cap) A.cand_pos[idx] = pos;
 }
 
 #define MAXBLK (MK_MAX_TILE / 32)
@@ -290,7 +289,6 @@ struct StreamSmem {
     u32 cpre[3][MAXCHUNK];       // '\n' bytes before each chunk inside the tile
     u32 posmask[2][MAXBLK];      // double buffered: tile being probed / tile being masked
     uint16_t items[2][MAXBLK];
-    uint16_t hitq[MK_HITCAP];
     u64 bar[3];
     u64 P[3];                    // '\n' bytes before each staged tile (line number of its first byte)
     u32 tile[3];                 // ticket held by each stage
@@ -298,7 +296,7 @@ struct StreamSmem {
     u32 scur[3];                 // scan-chunk cursor per stage
     u32 sdone[3];                // scanned chunks per stage
     u32 n_items[2];              // items per buffer
-    u32 icur, bdone, mcur, nhits;
+    u32 icur, bdone, mcur;
     volatile u32 resolved;       // iteration stamp: line number of `next` is available
 };
 
@@ -321,7 +319,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
     if (tid == 0) {
         for (int s = 0; s < 3; s++) { mbar_init(&S.bar[s], 1); S.scur[s] = 0; S.sdone[s] = 0; S.tot[s] = 0; S.P[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.n_items[0] = 0; S.n_items[1] = 0; S.icur = 0; S.bdone = 0; S.mcur = 0; S.nhits = 0; S.resolved = 0;
+        S.n_items[0] = 0; S.n_items[1] = 0; S.icur = 0; S.bdone = 0; S.mcur = 0; S.resolved = 0;
     }
     __syncthreads();
 
@@ -423,35 +421,39 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
                 u32 total = __shfl_sync(0xffffffffu, incl, 15);   // NCHUNK <= 12 lanes carry values
                 if (lane == 0) {
                     S.tot[stage] = total;
-                    st_volatile_u64(&A.tile_desc[t], ((t == 0 ? 2ull : 1ull) << 62) | (u64)total);
+                    st_volatile_u64(&A.tile_desc[t], (1ull << 62) | (u64)total);
                     if (total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
                 }
             }
         }
     };
-    // exclusive prefix of tile t's newline count (warp 0, all lanes); publishes the inclusive value
+    // Line number of tile t (warp 0, all lanes).  This CTA resolved tile prev_t < t earlier, so
+    //   newlines before t = newlines through prev_t + sum of the counts of tiles prev_t+1 .. t-1,
+    // and every one of those counts was published when its tile was scanned, i.e. at least one
+    // iteration before this call.  All loads are independent: one L2 round trip, no chaining on
+    // other tiles' prefixes.
+    long long prev_t = -1;
+    u64 prev_incl = 0;
     auto resolve_tile = [&](u32 t, u32 total) -> u64 {
         const u64 VMASK = (1ull << 62) - 1;
-        if (t == 0) return 0;
-        u64 excl = 0;
-        long long look = (long long)t - 1;
-        for (;;) {
-            long long idx = look - (long long)lane;
-            u64 d;
-            do {
-                d = idx >= 0 ? ld_volatile_u64(&A.tile_desc[idx]) : (2ull << 62);
-            } while (__any_sync(0xffffffffu, (d >> 62) == 0));
-            u32 m2 = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-            u64 val = d & VMASK;
-            if (m2) {
-                u32 first = __ffs(m2) - 1;
-                excl += warp_sum_u64(lane <= first ? val : 0);
-                break;
+        u64 sum = 0;
+        for (long long i0 = prev_t + 1; i0 < (long long)t; i0 += 128) {
+            u64 d[4];
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                long long idx = i0 + 32 * k4 + (long long)lane;
+                d[k4] = idx < (long long)t ? ld_volatile_u64(&A.tile_desc[idx]) : (1ull << 62);
             }
-            excl += warp_sum_u64(val);
-            look -= 32;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; k4++) {
+                long long idx = i0 + 32 * k4 + (long long)lane;
+                while ((d[k4] >> 62) == 0) d[k4] = ld_volatile_u64(&A.tile_desc[idx]);
+                sum += d[k4] & VMASK;
+            }
         }
-        if (lane == 0) st_volatile_u64(&A.tile_desc[t], (2ull << 62) | ((excl + total) & VMASK));
+        u64 excl = prev_incl + warp_sum_u64(sum);
+        prev_t = (long long)t;
+        prev_incl = excl + total;
         return excl;
     };
     // M units: sequence-byte masks + item list of the tile in `stage`, into buffer `buf`
@@ -558,53 +560,55 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
                     u32 j = __ffs(hits) - 1;
                     hits &= hits - 1;
                     if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
-                    u32 pos = 32 * b + j;
-                    u32 slot = atomicAdd(&S.nhits, 1u);
-                    if (slot < MK_HITCAP) {
-                        S.hitq[slot] = (uint16_t)pos;
-                    } else {                               // queue full: finish this hit in place
-                        u64 code;
-                        if (verify_kmer(tx + MK_HALO + pos, A.kp, A.ptab, &code))
-                            emit_candidate(A, code, A.pos_base + T + pos);
-                    }
+                    emit_hit(A, T + 32 * b + j);
                 }
             }
         }
-        {   // last warp out: verify the queued hits, then recycle the stage of `cur`
+        {   // last warp out recycles the stage of `cur`
             u32 d = 0;
             __syncwarp();
             if (lane == 0) { __threadfence_block(); d = atomicAdd(&S.bdone, 1u); }
             d = __shfl_sync(0xffffffffu, d, 0);
-            if (d == NWARPS - 1) {
-                __threadfence_block();
-                u32 nh = S.nhits;
-                if (nh > MK_HITCAP) nh = MK_HITCAP;
-                for (u32 h = lane; h < nh; h += 32) {
-                    u32 pos = S.hitq[h];
-                    u64 code;
-                    if (verify_kmer(tx + MK_HALO + pos, A.kp, A.ptab, &code))
-                        emit_candidate(A, code, A.pos_base + T + pos);
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    S.n_items[buf] = 0; S.icur = 0; S.bdone = 0; S.nhits = 0;
-                    claim_and_load(stage);
-                }
+            if (d == NWARPS - 1 && lane == 0) {
+                S.n_items[buf] = 0; S.icur = 0; S.bdone = 0;
+                claim_and_load(stage);
             }
         }
-        // ---- M units of the next tile (after its line number is known) -------------------------
-        while (S.resolved != iter) {}
-        __threadfence_block();
-        mask_units(st1, buf ^ 1);
         // ---- S units of the tile two ahead -----------------------------------------------------
         {
             u32 par = st2 == 0 ? (uses0 & 1u) : (st2 == 1 ? (uses1 & 1u) : (uses2 & 1u));
             scan_units(st2, par);
             if (st2 == 0) uses0++; else if (st2 == 1) uses1++; else uses2++;
         }
+        // ---- M units of the next tile (after its line number is known) -------------------------
+        while (S.resolved != iter) {}
+        __threadfence_block();
+        mask_units(st1, buf ^ 1);
         stage = st1;
         buf ^= 1;
     }
+}
+
+// ---- exact verification of the hit list -------------------------------------------------------
+// One thread per position that passed the shared-memory filter (true members of the pass set
+// plus ~0.025 % Bloom false positives): the TL bytes ending there must all be ACGT — hence lie
+// inside one line — and the canonical k-mer's inner substring must be in the pass set
+// (iseq2comem.c:682-699).  Writes the sketch code (or EMPTY for a rejected hit) and the global
+// position.  Text comes from global memory: ~10 hits per 24 KB tile, mostly L2 hits.
+__global__ void __launch_bounds__(256)
+k_verify(const uint8_t *__restrict__ text, u64 n, u64 pos_base, KParams kp, const u64 *__restrict__ ptab,
+         u64 *__restrict__ cand_code, u64 *__restrict__ cand_pos)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u64 pos = cand_pos[i];
+    u64 code = ~0ull;
+    if (pos + 1 >= (u64)kp.TL) {
+        u64 c;
+        if (verify_kmer(text + pos, kp, ptab, &c)) code = c;
+    }
+    cand_code[i] = code;
+    cand_pos[i] = pos_base + pos;
 }
 
 // ---- tail rule ---------------------------------------------------------------------------------
@@ -737,9 +741,10 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     u64 *desc, *counters;
     CKR(mk_scratch(ctx, SB_TILE_DESC, (size_t)n_tiles, &desc));
     CKR(mk_scratch(ctx, SB_COUNTERS, 8, &counters));
-    double rate = (double)kp.dim_end / (double)(1ull << (4 * kp.subk));
+    // hit list capacity: members of S ∪ revcomp(S) (2 x pass rate) plus filter false positives
+    double rate = 2.0 * (double)kp.dim_end / (double)(1ull << (4 * kp.subk)) + 0.001;
     if (rate > 1.0) rate = 1.0;
-    u64 cap = (u64)((double)nbytes * rate * 1.25) + 65536;
+    u64 cap = (u64)((double)nbytes * rate * 0.75) + 65536;
     size_t smem = stream_smem_bytes(ctx->bitmap_words * 4);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
@@ -779,6 +784,11 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         if (h[0] > cap) { // candidate buffer too small: size it exactly and run again
             cap = h[0] + 1024;
             continue;
+        }
+        if (h[0]) {
+            k_verify<<<(unsigned)((h[0] + 255) / 256), 256, 0, ctx->stream>>>(d_text, h[0], pos_base, kp, ctx->d_ptab, cc, cp);
+            LAUNCH_COUNT(ctx);
+            CK(cudaGetLastError());
         }
         *n_cand = h[0];
         if (n_newlines) *n_newlines = raw_mode ? line_base : h[1];

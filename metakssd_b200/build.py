@@ -32,6 +32,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
                "-Xcompiler", "-fPIC,-Wno-format-truncation", "-I" + os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+        cmd += os.environ.get("MK_NVCC_FLAGS", "").split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -358,3 +358,12 @@ extern "C" int mk_fasta_co_file(mk_ctx *ctx, const char *path, const char *pipec
     uint64_t off[2] = {0, (uint64_t)buf.size()};
     return mk_fasta_co_host(ctx, buf.data(), off, 1, out);
 }
+
+// development aid (not part of the public header): device buffer of 64 * warps * 8 u64 receiving
+// clock64() stamps of CTA 0's first 64 iterations; nullptr disables.
+extern "C" int mk_debug_set_trace(mk_ctx *ctx, void *d_buf)
+{
+    if (!ctx) return MK_ERR_ARG;
+    ctx->d_trace = d_buf;
+    return MK_OK;
+}

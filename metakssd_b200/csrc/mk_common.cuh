@@ -14,7 +14,9 @@ typedef unsigned int u32;
 
 #define MK_HALO 32            // bytes of left context staged in front of every text tile
 #define MK_MAX_TILE 24576     // tile-proper bytes (multiple of 64); three stages fit beside the bitmap
+#ifndef MK_STREAM_THREADS
 #define MK_STREAM_THREADS 512
+#endif
 #define MK_HITCAP 1024        // first-level bitmap hits queued per tile
 
 // ---- sketch parameters mirrored on the device (values of iseq2comem.c:54-86) -------------------
@@ -59,6 +61,7 @@ struct mk_ctx {
     u32 *d_bitmap = nullptr;
     u32 bitmap_words = 0;
     u64 *d_ptab = nullptr;
+    void *d_trace = nullptr;        // development aid: phase timestamps of CTA 0 (mk_debug_set_trace)
     Scratch sb[SB_NUM];
     void *h_pinned = nullptr;       // small pinned staging block
     size_t h_pinned_bytes = 0;

@@ -129,7 +129,7 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
     CKR(mk_scratch(ctx, SB_IT_CODE, (size_t)n + 1, &it_key));
     CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n + 1, &it_cnt));
     CKR(mk_scratch(ctx, SB_IT_POS, (size_t)n + 1, &it_pos));
-    CKR(mk_scratch(ctx, SB_COUNTERS, 8, &counters));
+    CKR(mk_scratch(ctx, SB_COUNTERS, 16, &counters));
     CK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(minpos, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(cnt, 0, (size_t)cap * 4, ctx->stream));

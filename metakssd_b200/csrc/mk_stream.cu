@@ -38,11 +38,15 @@ struct StreamArgs {
     u64 cand_cap;
     u32 *flags;
     u64 *total_newlines;
+    u64 *trace;             // optional per-warp phase timestamps of CTA 0 (development aid)
+    u64 *wd;                // watchdog diagnostics: [site, block, warp, a, b, c, d, e]
     KParams kp;
 };
 
 #define TBUF_STRIDE (MK_HALO + MK_MAX_TILE + 96) // keeps the stage buffers 128-byte aligned
 #define FLAG_LONG_LINE 2u
+#define FLAG_WATCHDOG 4u     // a wait inside k_stream gave up (diagnostics in StreamArgs::wd)
+#define WD_LIMIT (1u << 21)
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
@@ -66,9 +70,11 @@ __device__ __forceinline__ u32 mbar_try_wait(u64 *bar, u32 parity)
         : "memory");
     return ok;
 }
-__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity)
+__device__ __forceinline__ bool mbar_wait(u64 *bar, u32 parity)
 {
-    while (!mbar_try_wait(bar, parity)) {}
+    for (u32 n = 0; !mbar_try_wait(bar, parity); n++)
+        if (n > WD_LIMIT) return false;
+    return true;
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
     const u32 TB = A.tile_bytes;
     const u32 NBLK = TB / 32;
     const u32 NCHUNK = (TB + 2047u) / 2048u;
-    const u32 NMUNIT = (NBLK + 31u) / 32u;
+    const u32 NMUNIT = (NBLK + 63u) / 64u;
     auto tile_len = [&](u32 t) -> u32 {
         u64 rem = A.nbytes - (u64)t * TB;
         return rem < TB ? (u32)rem : TB;
@@ -347,6 +353,11 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         mbar_expect_tx(&S.bar[stage], bytes);
         tma_load_1d(dst, src, bytes, &S.bar[stage]);
     };
+    auto watchdog = [&](u32 site, u64 a, u64 b, u64 c, u64 d) {
+        if (atomicOr(A.flags, FLAG_WATCHDOG) & FLAG_WATCHDOG) return;   // first report wins
+        A.wd[0] = site; A.wd[1] = blockIdx.x; A.wd[2] = wid; A.wd[3] = a; A.wd[4] = b; A.wd[5] = c; A.wd[6] = d;
+        A.wd[7] = ((u64)S.tile[0] << 42) | ((u64)S.tile[1] << 21) | (u64)S.tile[2];
+    };
     // S units: scan the tile in `stage` (chunks pulled dynamically by whole warps).
     auto scan_units = [&](int stage, u32 use_parity) {
         const u32 t = S.tile[stage];
@@ -359,7 +370,10 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
             if (lane == 0) c = atomicAdd(&S.scur[stage], 1u);
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= NCHUNK) break;
-            if (!waited) { mbar_wait(&S.bar[stage], use_parity); waited = true; }
+            if (!waited) {
+                if (!mbar_wait(&S.bar[stage], use_parity) && lane == 0) watchdog(1, stage, use_parity, t, c);
+                waited = true;
+            }
             const u32 off = c * 2048u + lane * 64u;        // my 64 bytes (two blocks)
             // blank what lies outside the text so that stale bytes can never look like sequence
             if (t == 0 && c == 0 && lane < MK_HALO / 4) reinterpret_cast<u32 *>(tx)[lane] = 0;
@@ -447,7 +461,11 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 #pragma unroll
             for (int k4 = 0; k4 < 4; k4++) {
                 long long idx = i0 + 32 * k4 + (long long)lane;
-                while ((d[k4] >> 62) == 0) d[k4] = ld_volatile_u64(&A.tile_desc[idx]);
+                for (u32 n = 0; (d[k4] >> 62) == 0; n++) {
+                    if (n > WD_LIMIT) { watchdog(2, t, (u64)idx, (u64)prev_t, 0); break; }
+                    __nanosleep(100);
+                    d[k4] = ld_volatile_u64(&A.tile_desc[idx]);
+                }
                 sum += d[k4] & VMASK;
             }
         }
@@ -456,45 +474,54 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         prev_incl = excl + total;
         return excl;
     };
-    // M units: sequence-byte masks + item list of the tile in `stage`, into buffer `buf`
-    auto mask_units = [&](int stage, int buf) {
+    // M units: sequence-byte masks + item list of the tile in `stage`, into buffer `buf`.
+    // A unit is 64 consecutive blocks (two per lane), pulled dynamically.
+    auto mask_units = [&](int stage, int buf, bool all_warps) {
         const u32 t = S.tile[stage];
         if (t >= A.n_tiles) return;
         const u32 tb = tile_len(t);
         const u32 P = RAW ? 0u : (u32)S.P[stage];
+        (void)all_warps;
         for (;;) {
             u32 u = 0;
             if (lane == 0) u = atomicAdd(&S.mcur, 1u);
             u = __shfl_sync(0xffffffffu, u, 0);
             if (u >= NMUNIT) break;
-            const u32 b = u * 32u + lane;
-            u32 pm = 0;
-            if (b < NBLK) {
-                if (RAW) {
-                    u32 lo = 32 * b;
-                    pm = lo >= tb ? 0u : (tb - lo >= 32 ? 0xffffffffu : ((1u << (tb - lo)) - 1u));
-                } else {
-                    // line(i) = P + '\n' before the block + '\n' among bytes < i of the block; a byte is a
-                    // sequence byte iff line(i) % 4 == 1 and it is not the '\n' itself.  The two low bits
-                    // of the running count are prefix parities of the newline mask.
-                    const u32 nl = S.nlm[stage][b];
-                    const u32 s0 = (P + S.cpre[stage][b >> 6] + S.exw[stage][b]) & 3u;
-                    const u32 tgt = (1u - s0) & 3u;              // count % 4 that puts a byte on phase 1
-                    u32 p0 = 0, p1 = 0;
-                    if (nl) {
-                        p0 = prefix_xor(nl << 1);                // parity of '\n' strictly before each byte
-                        p1 = prefix_xor((nl & p0) << 1);         // carries out of bit 0
+            u32 pm[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const u32 b = u * 64u + 32u * h + lane;
+                pm[h] = 0;
+                if (b < NBLK) {
+                    if (RAW) {
+                        u32 lo = 32 * b;
+                        pm[h] = lo >= tb ? 0u : (tb - lo >= 32 ? 0xffffffffu : ((1u << (tb - lo)) - 1u));
+                    } else {
+                        // line(i) = P + '\n' before the block + '\n' among bytes < i of the block; a byte is
+                        // a sequence byte iff line(i) % 4 == 1 and it is not the '\n' itself.  The two low
+                        // bits of the running count are prefix parities of the newline mask.
+                        const u32 nl = S.nlm[stage][b];
+                        const u32 s0 = (P + S.cpre[stage][b >> 6] + S.exw[stage][b]) & 3u;
+                        const u32 tgt = (1u - s0) & 3u;          // count % 4 that puts a byte on phase 1
+                        u32 p0 = 0, p1 = 0;
+                        if (nl) {
+                            p0 = prefix_xor(nl << 1);            // parity of '\n' strictly before each byte
+                            p1 = prefix_xor((nl & p0) << 1);     // carries out of bit 0
+                        }
+                        pm[h] = (p0 ^ ((tgt & 1u) ? 0u : ~0u)) & (p1 ^ ((tgt & 2u) ? 0u : ~0u)) & ~nl;
                     }
-                    pm = (p0 ^ ((tgt & 1u) ? 0u : ~0u)) & (p1 ^ ((tgt & 2u) ? 0u : ~0u)) & ~nl;
+                    S.posmask[buf][b] = pm[h];
                 }
-                S.posmask[buf][b] = pm;
             }
-            const bool act = pm != 0;
-            const u32 m = __ballot_sync(0xffffffffu, act);
+            const u32 m0 = __ballot_sync(0xffffffffu, pm[0] != 0);
+            const u32 m1 = __ballot_sync(0xffffffffu, pm[1] != 0);
+            const u32 n0 = __popc(m0);
             u32 base = 0;
-            if (lane == 0 && m) base = atomicAdd(&S.n_items[buf], (u32)__popc(m));
+            if (lane == 0 && (m0 | m1)) base = atomicAdd(&S.n_items[buf], n0 + (u32)__popc(m1));
             base = __shfl_sync(0xffffffffu, base, 0);
-            if (act) S.items[buf][base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)b;
+            const u32 lt = (1u << lane) - 1u;
+            if (pm[0]) S.items[buf][base + __popc(m0 & lt)] = (uint16_t)(u * 64u + lane);
+            if (pm[1]) S.items[buf][base + n0 + __popc(m1 & lt)] = (uint16_t)(u * 64u + 32u + lane);
         }
     };
 
@@ -514,7 +541,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         }
     }
     __syncthreads();
-    mask_units(0, 0);
+    mask_units(0, 0, true);
 
     int stage = 0, buf = 0;
     u32 iter = 0;
@@ -529,6 +556,9 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         const u64 T = (u64)cur * TB;
         const u32 n_items = S.n_items[buf];
         if (tid == 0) S.mcur = 0;                          // nobody pulls M units before `resolved` is stamped
+        const bool tr = A.trace && blockIdx.x == 0 && iter <= 64 && lane == 0;
+        u64 *trp = A.trace + ((u64)(iter - 1) * NWARPS + wid) * 8;
+        if (tr) { trp[0] = clock64(); trp[6] = n_items; trp[7] = cur; }
 
         // warp 0: line number of the next tile, then stamp it
         if (wid == 0) {
@@ -543,6 +573,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
             __syncwarp();
             if (lane == 0) { __threadfence_block(); S.resolved = iter; }
         }
+        if (tr) trp[1] = clock64();
 
         // ---- P units ---------------------------------------------------------------------------
         for (;;) {
@@ -564,6 +595,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
                 }
             }
         }
+        if (tr) trp[2] = clock64();
         {   // last warp out recycles the stage of `cur`
             u32 d = 0;
             __syncwarp();
@@ -580,10 +612,16 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
             scan_units(st2, par);
             if (st2 == 0) uses0++; else if (st2 == 1) uses1++; else uses2++;
         }
+        if (tr) trp[3] = clock64();
         // ---- M units of the next tile (after its line number is known) -------------------------
-        while (S.resolved != iter) {}
+        for (u32 n = 0; S.resolved != iter; n++) {
+            if (n > WD_LIMIT) { if (lane == 0) watchdog(3, iter, S.resolved, cur, S.tile[st1]); break; }
+            __nanosleep(40);
+        }
+        if (tr) trp[4] = clock64();
         __threadfence_block();
-        mask_units(st1, buf ^ 1);
+        mask_units(st1, buf ^ 1, false);
+        if (tr) trp[5] = clock64();
         stage = st1;
         buf ^= 1;
     }
@@ -740,7 +778,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
 
     u64 *desc, *counters;
     CKR(mk_scratch(ctx, SB_TILE_DESC, (size_t)n_tiles, &desc));
-    CKR(mk_scratch(ctx, SB_COUNTERS, 8, &counters));
+    CKR(mk_scratch(ctx, SB_COUNTERS, 16, &counters));
     // hit list capacity: members of S ∪ revcomp(S) (2 x pass rate) plus filter false positives
     double rate = 2.0 * (double)kp.dim_end / (double)(1ull << (4 * kp.subk)) + 0.001;
     if (rate > 1.0) rate = 1.0;
@@ -753,30 +791,39 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         CKR(mk_scratch(ctx, SB_CAND_CODE, (size_t)cap, &cc));
         CKR(mk_scratch(ctx, SB_CAND_POS, (size_t)cap, &cp));
         CK(cudaMemsetAsync(desc, 0, (size_t)n_tiles * 8, ctx->stream));
-        CK(cudaMemsetAsync(counters, 0, 64, ctx->stream));
+        CK(cudaMemsetAsync(counters, 0, 128, ctx->stream));
         StreamArgs a;
         a.text = d_text; a.nbytes = nbytes; a.pos_base = pos_base; a.line_base = line_base;
         a.tile_bytes = tile_bytes; a.n_tiles = n_tiles; a.tile_desc = desc;
         a.cand_count = counters + 0; a.total_newlines = counters + 1;
         a.tile_counter = (u32 *)(counters + 2); a.flags = (u32 *)(counters + 2) + 1;
         a.bitmap = ctx->d_bitmap; a.bitmap_bytes = ctx->bitmap_words * 4; a.ptab = ctx->d_ptab; a.two_hash = ctx->kp.mw >= 22 ? 1u : 0u;
-        a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp;
+        a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp; a.trace = (u64 *)ctx->d_trace; a.wd = counters + 8;
         u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         kern<<<grid, MK_STREAM_THREADS, smem, ctx->stream>>>(a);
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         LAUNCH_COUNT(ctx);
         CK(cudaGetLastError());
-        u64 h[4];
-        CK(cudaMemcpyAsync(h, counters, 32, cudaMemcpyDeviceToHost, ctx->stream));
+        u64 h[16];
+        CK(cudaMemcpyAsync(h, counters, 128, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->prof.d2h_bytes += 32;
+        ctx->prof.d2h_bytes += 128;
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
         ctx->prof.stream_kernel_ms += ms;
         ctx->prof.stream_kernel_launches++;
         ctx->prof.stream_kernel_bytes += nbytes;
         u32 flags = (u32)(h[2] >> 32);
+        if (flags & FLAG_WATCHDOG) {
+            snprintf(ctx->err, sizeof(ctx->err),
+                     "k_stream watchdog: site %llu block %llu warp %llu a=%llu b=%llu c=%llu d=%llu tiles=%llu/%llu/%llu n_tiles=%u",
+                     (unsigned long long)h[8], (unsigned long long)h[9], (unsigned long long)h[10],
+                     (unsigned long long)h[11], (unsigned long long)h[12], (unsigned long long)h[13],
+                     (unsigned long long)h[14], (unsigned long long)(h[15] >> 42),
+                     (unsigned long long)((h[15] >> 21) & 0x1FFFFF), (unsigned long long)(h[15] & 0x1FFFFF), n_tiles);
+            return MK_ERR_CUDA;
+        }
         if (!raw_mode && (flags & FLAG_LONG_LINE)) {
             snprintf(ctx->err, sizeof(ctx->err), "FASTQ line longer than 4095 bytes");
             return MK_ERR_LONG_LINE;

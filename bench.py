@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py — L3K11 `dist -A` sketching + `composite` throughput on B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one pass of the hot path over the whole synthetic metagenome of this rank
+(BASELINE.json configs[1]: 40 M interleaved 150-bp records = 6 Gbp per GPU, 1 000-species
+MarkerDB): FASTQ text -> sketch codes + counts in reference slot order -> per-species coverage
+statistics.  Prints ONE JSON line (rank 0).
+
+  value     whole-job Gbp/s with the FASTQ text already resident in HBM
+  e2e       same through the host-buffer entry point (pinned host text, H2D inside the timed region,
+            statistics read back)
+  roofline  dominant kernel (k_stream): algorithmic bytes (sequence bytes + their newlines, SURVEY
+            §8(d)) / average launch duration measured with CUDA events on the library's stream,
+            against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the reference binary (oracle/_ref/metakssd, all host cores) on a bounded sample
+
+`--impl reference` times the unmodified reference binary on bounded samples of the same workload.
+With N > 1 (torchrun) every rank sketches its own 6 Gbp shard (weak scaling); runs are exchanged by
+code range with an NCCL all-to-all and rank 0 orders and reports.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+K, SUBK, L = 11, 6, 3
+SEED = 0x4D4B5353
+READ_LEN = 150
+METRIC = "L3K11 -A sketching + composite throughput"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=40_000_000, help="FASTQ records per GPU (configs[1]: 40 M)")
+    ap.add_argument("--species", type=int, default=1000)
+    ap.add_argument("--genome-len", type=int, default=5_000_000)
+    ap.add_argument("--cpu-reads", type=int, default=3_000_000, help="records of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 6:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def workload_name(args):
+    return ("synthetic %d M x %d bp interleaved paired-end FASTQ per GPU (%.1f Gbp), L3K11 -A sketch + composite vs "
+            "%d-species synthetic MarkerDB" % (args.reads // 1_000_000, READ_LEN, args.reads * READ_LEN / 1e9,
+                                               args.species))
+
+
+# =====================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import metakssd_b200 as M
+    from metakssd_b200 import workload as W
+    from metakssd_b200 import distributed as D
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    shuf_id, perm = M.make_shuf(SEED ^ 1, SUBK)
+    sk = M.Sketcher(perm, K, SUBK, L, device=local)
+    spec = M.synth_spec(SEED ^ 2, args.species, args.genome_len, READ_LEN)
+    t0 = time.time()
+    mdb = W.build_markerdb(sk, spec)
+    t_mdb = time.time() - t0
+
+    r0, r1 = rank * args.reads, (rank + 1) * args.reads
+    nbytes = spec.fastq_bytes(r0, r1)
+    pos_base = spec.fastq_bytes(0, r0)
+    d_text = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+    sk.synth_fastq_device(spec.P, spec.cdf32, spec.species, r0, r1, d_text, d_text.numel())
+    bases = args.reads * READ_LEN
+    algo_bytes = args.reads * (READ_LEN + 1)          # sequence bytes + their '\n' 
+
+    lib_stream = torch.cuda.ExternalStream(sk.cuda_stream(), device=dev)
+
+    def composite(sketch):
+        qry = [(sketch.codes[c], sketch.counts[c]) for c in range(len(sketch.codes))]
+        stats = sk.composite(mdb.comp, qry)
+        return M.composite_tsv("reads.fq", mdb.names, stats)
+
+    def step_device():
+        if world == 1:
+            return composite(sk.fastq_koc_device(d_text, nbytes))
+        s = D.sketch_sharded(sk, d_text, nbytes, pos_base, 0, rank == world - 1)
+        return composite(s) if rank == 0 else None
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(lib_stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record(lib_stream)
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    sampler = ClockSampler(local)
+    sk.profile(reset=True)
+    if rank == 0:
+        sampler.start()
+    # warm-up outside the profile window
+    ms_total, tsv = timed(step_device, 0, args.warmup)
+    sk.profile(reset=True)
+    ms_total, tsv = timed(step_device, args.steps, 0)
+    prof = sk.profile()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = world * bases / 1e9 / (ms_step / 1e3)
+
+    # ---- end to end: pinned host text -> H2D -> sketch -> composite -> statistics on the host -----
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        need = nbytes * world * 1.15
+        e2e_reads = args.reads
+        if psutil.virtual_memory().available < need + (8 << 30):
+            e2e_reads = max(1_000_000, int(args.reads * (psutil.virtual_memory().available * 0.5) / need))
+        e_nbytes = spec.fastq_bytes(r0, r0 + e2e_reads)
+        h_text = torch.empty(e_nbytes, dtype=torch.uint8, pin_memory=True)
+        h_text.copy_(d_text[:e_nbytes])
+        torch.cuda.synchronize(dev)
+
+        def step_host():
+            if world == 1:
+                return composite(sk.fastq_koc_host(h_text))
+            # multi-GPU: the shard goes through the same host-buffer upload, then the sharded path
+            d_text[:e_nbytes].copy_(h_text, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            s = D.sketch_sharded(sk, d_text, e_nbytes, pos_base, 0, rank == world - 1)
+            return composite(s) if rank == 0 else None
+
+        e_steps = max(2, min(args.steps, 3))
+        ms_e, tsv_e = timed(step_host, e_steps, 1)
+        ms_e /= e_steps
+        e2e = {"value": world * e2e_reads * READ_LEN / 1e9 / (ms_e / 1e3), "unit": "Gbp/s",
+               "h2d_bytes_per_step": int(e_nbytes + mdb.n_codes * 4 + (args.species + 1) * 8),
+               "d2h_bytes_per_step": int(24 * args.species + 6 * 200_000),
+               "ms_per_step": ms_e, "reads_per_gpu": e2e_reads}
+        del h_text
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    launches = max(1, int(prof.stream_kernel_launches))
+    k_ms = prof.stream_kernel_ms / launches
+    achieved = algo_bytes / 1e9 / (k_ms / 1e3)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_stream_traffic.json")))
+        traffic = tj["dram_bytes_per_text_byte"] * nbytes
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "k_stream", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                "text_bytes_per_launch": nbytes, "kernel_share_of_step": k_ms / ms_step,
+                "kernel_Gbp_s": bases / 1e9 / (k_ms / 1e3)}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, sk, spec, shuf_id, perm, mdb, d_text)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "k": K, "subk": SUBK, "L": L, "reads_per_gpu": args.reads,
+                   "read_len": READ_LEN, "species": args.species, "genome_len": args.genome_len,
+                   "markerdb_codes": mdb.n_codes, "l2_policy": "input (%.1f GB per GPU) is far larger than L2" % (nbytes / 1e9),
+                   "parallelism": "reads sharded per GPU, runs exchanged by code range (all-to-all)" if world > 1 else "1 GPU",
+                   "markerdb_build_s": t_mdb, "species_reported": tsv.count("\n") if tsv else 0},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(prof.kernel_launches), "clocks": clocks,
+        "breakdown_ms_per_step": {"stream_kernel": prof.stream_kernel_ms / args.steps, "reduce_order": prof.reduce_ms / args.steps,
+                                  "composite": prof.composite_ms / args.steps},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# =====================================================================================================
+def _write_sample(args, sk, spec, d_text, n_reads, workdir):
+    """First n_reads records of the device-resident FASTQ -> file (page cache / tmpfs)."""
+    nb = spec.fastq_bytes(0, n_reads)
+    path = os.path.join(workdir, "reads.fq")
+    with open(path, "wb") as f:
+        CH = 256 << 20
+        for o in range(0, nb, CH):
+            f.write(d_text[o:min(nb, o + CH)].cpu().numpy().tobytes())
+    return path, nb
+
+
+def _write_markerdb(mdb, shuf_id, workdir, info):
+    import metakssd_b200 as M
+    path = os.path.join(workdir, "markerdb")
+
+    class _S:  # one "sketch" per species for write_sketch_dir
+        def __init__(self, codes):
+            self.codes = codes
+            self.counts = None
+
+        @property
+        def n_total(self):
+            return int(sum(c.size for c in self.codes))
+
+    sk_list = []
+    S = len(mdb.names)
+    for s in range(S):
+        sk_list.append(_S([mdb.comp[c][0][int(mdb.comp[c][1][s]):int(mdb.comp[c][1][s + 1])] for c in range(len(mdb.comp))]))
+    M.write_sketch_dir(path, shuf_id, info, mdb.names, sk_list, koc=False)
+    return path
+
+
+def _ref_bin():
+    p = os.path.join(ROOT, "oracle", "_ref", "metakssd")
+    return p if os.path.exists(p) else None
+
+
+def _time_reference(ref, shuf_path, fq_path, mdb_path, workdir, threads):
+    """wall seconds of `dist -A` and of `composite` with the reference binary."""
+    out = os.path.join(workdir, "qry_sketch")
+    shutil.rmtree(out, ignore_errors=True)
+    t0 = time.perf_counter()
+    subprocess.run([ref, "dist", "-L", shuf_path, "-A", "-p", str(threads), "-o", out, fq_path], check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    t1 = time.perf_counter()
+    r = subprocess.run([ref, "composite", "-r", mdb_path, "-q", out, "-p", str(threads)], check=True,
+                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL)
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, r.stdout
+
+
+def cpu_baseline(args, sk, spec, shuf_id, perm, mdb, d_text):
+    import metakssd_b200 as M
+    threads = os.cpu_count() or 1
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    workdir = tempfile.mkdtemp(prefix="mkssd_cpu_", dir=base)
+    try:
+        n = min(args.cpu_reads, args.reads)
+        fq, nb = _write_sample(args, sk, spec, d_text, n, workdir)
+        ref = _ref_bin()
+        if ref:
+            shuf_path = os.path.join(workdir, "L3K11.shuf")
+            M.write_shuf(shuf_path, shuf_id, K, SUBK, L, perm)
+            mdb_path = _write_markerdb(mdb, shuf_id, workdir, sk.info)
+            best = None
+            for _ in range(2):
+                td, tc, _ = _time_reference(ref, shuf_path, fq, mdb_path, workdir, threads)
+                if best is None or td + tc < best[0] + best[1]:
+                    best = (td, tc)
+            return {"value": n * READ_LEN / 1e9 / (best[0] + best[1]), "unit": "Gbp/s", "cores": threads,
+                    "kind": "reference", "sample": "first %d records (%.2f Gbp, %.0f MB FASTQ) of the bench workload, "
+                    "`metakssd dist -L L3K11.shuf -A -p %d` + `composite -p %d`, page cache warm, best of 2"
+                    % (n, n * READ_LEN / 1e9, nb / 1e6, threads, threads),
+                    "dist_s": best[0], "composite_s": best[1]}
+        import oracle as O
+        n = min(n, 300_000)
+        text = d_text[:spec.fastq_bytes(0, n)].cpu().numpy()
+        p = O.params(K, SUBK, L)
+        t0 = time.perf_counter()
+        O.fastq_koc(p, perm, text)
+        dt = time.perf_counter() - t0
+        return {"value": n * READ_LEN / 1e9 / dt, "unit": "Gbp/s", "cores": 1, "kind": "port",
+                "sample": "first %d records, single-threaded C restatement (oracle/kssd_oracle.c)" % n}
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+
+
+# =====================================================================================================
+def run_reference(args):
+    """The unmodified reference binary on bounded samples (all host cores)."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return
+    ref = _ref_bin()
+    import torch
+    import metakssd_b200 as M
+    from metakssd_b200 import workload as W
+    threads = os.cpu_count() or 1
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    workdir = tempfile.mkdtemp(prefix="mkssd_ref_", dir=base)
+    try:
+        # inputs come from the device generator (they are inputs, not the timed path)
+        shuf_id, perm = M.make_shuf(SEED ^ 1, SUBK)
+        sk = M.Sketcher(perm, K, SUBK, L, device=0)
+        spec = M.synth_spec(SEED ^ 2, args.species, args.genome_len, READ_LEN)
+        mdb = W.build_markerdb(sk, spec)
+        n = min(args.cpu_reads, args.reads)
+        nb = spec.fastq_bytes(0, n)
+        d_text = torch.empty(nb + 256, dtype=torch.uint8, device="cuda:0")
+        sk.synth_fastq_device(spec.P, spec.cdf32, spec.species, 0, n, d_text, d_text.numel())
+        fq, _ = _write_sample(args, sk, spec, d_text, n, workdir)
+        shuf_path = os.path.join(workdir, "L3K11.shuf")
+        M.write_shuf(shuf_path, shuf_id, K, SUBK, L, perm)
+        mdb_path = _write_markerdb(mdb, shuf_id, workdir, sk.info)
+        info = sk.info
+        sk.close()
+        del d_text
+        if ref is None:
+            import oracle as O
+            p = O.params(K, SUBK, L)
+            text = np.fromfile(fq, dtype=np.uint8)
+
+            def one():
+                t0 = time.perf_counter()
+                O.fastq_koc(p, perm, text)
+                return time.perf_counter() - t0
+            kind, cores = "port", 1
+        else:
+            def one():
+                td, tc, _ = _time_reference(ref, shuf_path, fq, mdb_path, workdir, threads)
+                return td + tc
+            kind, cores = "reference", threads
+        for _ in range(args.warmup):
+            one()
+        times = [one() for _ in range(args.steps)]
+        sec = sum(times) / len(times)
+        val = n * READ_LEN / 1e9 / sec
+        sample = ("each step: first %d records (%.2f Gbp) of the bench workload through `metakssd dist -L L3K11.shuf "
+                  "-A -p %d` + `composite -p %d` (reference binary built from /root/reference, page cache warm)"
+                  % (n, n * READ_LEN / 1e9, cores, cores))
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "Gbp/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": workload_name(args), "k": K, "subk": SUBK, "L": L, "read_len": READ_LEN,
+                           "species": args.species, "genome_len": args.genome_len, "sample_reads": n},
+                "cpu_baseline": {"value": val, "unit": "Gbp/s", "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+    finally:
+        shutil.rmtree(workdir, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -100,6 +100,9 @@ void mk_ctx_destroy(mk_ctx *ctx);
 int mk_ctx_info(const mk_ctx *ctx, mk_info *info);
 int mk_ctx_profile(mk_ctx *ctx, mk_profile *prof, int reset);
 int mk_ctx_synchronize(mk_ctx *ctx);
+/* The CUDA stream (cudaStream_t) all kernels and copies of this context are issued on, so that a
+ * caller can bracket calls with its own events. */
+void *mk_ctx_cuda_stream(mk_ctx *ctx);
 
 /* ---- FASTQ with k-mer counts (`dist -A`) ------------------------------------------------ */
 /* d_text: device pointer (16-byte aligned, readable up to the next 16-byte boundary past
@@ -179,6 +182,17 @@ int mk_synth_fastq_device(mk_ctx *ctx, const struct mks_params *P, const uint32_
  * file boundaries. */
 int mk_synth_fasta_device(mk_ctx *ctx, const struct mks_params *P, uint32_t s0, uint32_t s1, void *d_out,
                           size_t capacity, uint64_t *offsets);
+
+/* Host-side helpers of the generator: default parameters + abundance CDF (arrays are malloc'ed,
+ * release with mk_synth_free), text sizes, and a deterministic .shuf permutation (same file
+ * format as `metakssd shuffle`, seeded instead of srand(time)). */
+int mk_synth_build(struct mks_params *P, uint64_t seed, uint32_t n_species, uint32_t genome_len, uint32_t read_len,
+                   uint32_t **cdf32, uint32_t **species);
+void mk_synth_free(void *p);
+uint64_t mk_synth_fastq_bytes(const struct mks_params *P, uint64_t r0, uint64_t r1);
+uint64_t mk_synth_fasta_bytes(const struct mks_params *P, uint32_t s);
+void mk_synth_shuf_perm(uint64_t seed, int subk, int32_t *perm);
+int32_t mk_synth_shuf_id(uint64_t seed);
 
 #ifdef __cplusplus
 }

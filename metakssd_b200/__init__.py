@@ -5,7 +5,8 @@ The compute lives in libmkssd_b200.so (hand-written CUDA, C ABI in include/mkssd
 this package is the Python binding plus the host-side mirror of the reference's file formats.
 """
 from .api import (MkError, MkInfo, MksParams, MkProfile, Sketch, Sketcher, composite_tsv, device_count, load,
-                  read_shuf, read_sketch_dir, write_shuf, write_sketch_dir, EXPORTS, LIB_PATH)
+                  read_shuf, read_sketch_dir, write_shuf, write_sketch_dir, synth_spec, make_shuf, SynthSpec,
+                  EXPORTS, LIB_PATH)
 
 __all__ = ["MkError", "MkInfo", "MksParams", "MkProfile", "Sketch", "Sketcher", "composite_tsv", "device_count",
-           "load", "read_shuf", "read_sketch_dir", "write_shuf", "write_sketch_dir", "EXPORTS", "LIB_PATH"]
+           "load", "synth_spec", "make_shuf", "SynthSpec", "read_shuf", "read_sketch_dir", "write_shuf", "write_sketch_dir", "EXPORTS", "LIB_PATH"]

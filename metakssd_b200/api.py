@@ -82,11 +82,12 @@ class MksParams(C.Structure):  # include/mkssd_synth.h
 # every symbol include/mkssd_b200.h declares
 EXPORTS = [
     "mk_strerror", "mk_last_error", "mk_device_count", "mk_ctx_create", "mk_ctx_destroy", "mk_ctx_info",
-    "mk_ctx_profile", "mk_ctx_synchronize", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
+    "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
     "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_fastq_partial_device",
     "mk_runs_finalize_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
-    "mk_synth_fasta_device",
+    "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
+    "mk_synth_shuf_perm", "mk_synth_shuf_id",
 ]
 
 _lib = None
@@ -113,6 +114,8 @@ def load():
     L.mk_ctx_info.argtypes = [vp, C.POINTER(MkInfo)]
     L.mk_ctx_profile.argtypes = [vp, C.POINTER(MkProfile), i32]
     L.mk_ctx_synchronize.argtypes = [vp]
+    L.mk_ctx_cuda_stream.argtypes = [vp]
+    L.mk_ctx_cuda_stream.restype = vp
     L.mk_fastq_koc_device.argtypes = [vp, vp, sz, C.POINTER(MkSketch)]
     L.mk_fastq_koc_host.argtypes = [vp, vp, sz, C.POINTER(MkSketch)]
     L.mk_fastq_koc_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(MkSketch)]
@@ -131,12 +134,62 @@ def load():
     L.mk_count_newlines_device.argtypes = [vp, vp, sz, C.POINTER(u64)]
     L.mk_synth_fastq_device.argtypes = [vp, C.POINTER(MksParams), vp, vp, u64, u64, vp, sz, C.POINTER(sz)]
     L.mk_synth_fasta_device.argtypes = [vp, C.POINTER(MksParams), C.c_uint32, C.c_uint32, vp, sz, vp]
+    L.mk_synth_build.argtypes = [C.POINTER(MksParams), u64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                 C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_uint32))]
+    L.mk_synth_free.argtypes = [vp]
+    L.mk_synth_free.restype = None
+    L.mk_synth_fastq_bytes.argtypes = [C.POINTER(MksParams), u64, u64]
+    L.mk_synth_fastq_bytes.restype = u64
+    L.mk_synth_fasta_bytes.argtypes = [C.POINTER(MksParams), C.c_uint32]
+    L.mk_synth_fasta_bytes.restype = u64
+    L.mk_synth_shuf_perm.argtypes = [u64, i32, vp]
+    L.mk_synth_shuf_perm.restype = None
+    L.mk_synth_shuf_id.argtypes = [u64]
+    L.mk_synth_shuf_id.restype = C.c_int32
     _lib = L
     return L
 
 
 def device_count() -> int:
     return int(load().mk_device_count())
+
+
+# ------------------------------------------------------------------------------------ generator
+@dataclass
+class SynthSpec:
+    """Synthetic community (include/mkssd_synth.h): parameters + abundance CDF."""
+    P: MksParams
+    cdf32: np.ndarray
+    species: np.ndarray
+
+    def fastq_bytes(self, r0: int, r1: int) -> int:
+        return int(load().mk_synth_fastq_bytes(C.byref(self.P), r0, r1))
+
+    def fasta_bytes(self, s: int) -> int:
+        return int(load().mk_synth_fasta_bytes(C.byref(self.P), s))
+
+
+def synth_spec(seed: int, n_species: int, genome_len: int, read_len: int = 150) -> SynthSpec:
+    L = load()
+    P = MksParams()
+    cdf = C.POINTER(C.c_uint32)()
+    spc = C.POINTER(C.c_uint32)()
+    rc = L.mk_synth_build(C.byref(P), seed, n_species, genome_len, read_len, C.byref(cdf), C.byref(spc))
+    if rc != MK_OK:
+        raise MkError(rc, L.mk_strerror(rc).decode())
+    n = P.n_present
+    out = SynthSpec(P, np.ctypeslib.as_array(cdf, shape=(n,)).copy(), np.ctypeslib.as_array(spc, shape=(n,)).copy())
+    L.mk_synth_free(cdf)
+    L.mk_synth_free(spc)
+    return out
+
+
+def make_shuf(seed: int, subk: int):
+    """Deterministic .shuf content: (shuf_id, int32 permutation of 16^subk)."""
+    L = load()
+    perm = np.empty(1 << (4 * subk), dtype=np.int32)
+    L.mk_synth_shuf_perm(seed, subk, perm.ctypes.data)
+    return int(L.mk_synth_shuf_id(seed)), perm
 
 
 # ------------------------------------------------------------------------------------ .shuf files
@@ -227,6 +280,13 @@ class Sketcher:
     def _ck(self, rc: int):
         if rc != MK_OK:
             raise MkError(rc, self._L.mk_last_error(self._h).decode() or self._L.mk_strerror(rc).decode())
+
+    def cuda_stream(self) -> int:
+        """cudaStream_t of the context (wrap with torch.cuda.ExternalStream to record events on it)."""
+        return int(self._L.mk_ctx_cuda_stream(self._h) or 0)
+
+    def synchronize(self):
+        self._ck(self._L.mk_ctx_synchronize(self._h))
 
     def profile(self, reset: bool = False) -> MkProfile:
         p = MkProfile()

@@ -217,6 +217,8 @@ extern "C" int mk_ctx_synchronize(mk_ctx *ctx)
     return MK_OK;
 }
 
+extern "C" void *mk_ctx_cuda_stream(mk_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
 extern "C" void mk_sketch_free(mk_sketch *s)
 {
     if (!s) return;

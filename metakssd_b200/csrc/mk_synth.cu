@@ -99,3 +99,20 @@ extern "C" int mk_synth_fasta_device(mk_ctx *ctx, const struct mks_params *P, ui
     CK(cudaStreamSynchronize(ctx->stream));
     return MK_OK;
 }
+
+// ---- host-side helpers of the generator (thin wrappers over include/mkssd_synth.h) --------------
+extern "C" int mk_synth_build(struct mks_params *P, uint64_t seed, uint32_t n_species, uint32_t genome_len,
+                              uint32_t read_len, uint32_t **cdf32, uint32_t **species)
+{
+    if (!P || !cdf32 || !species || n_species == 0 || genome_len < read_len) return MK_ERR_ARG;
+    mks_default_params(P, seed, n_species, genome_len, read_len);
+    return mks_build_cdf(P, cdf32, species) == 0 ? MK_OK : MK_ERR_NOMEM;
+}
+extern "C" void mk_synth_free(void *p) { free(p); }
+extern "C" uint64_t mk_synth_fastq_bytes(const struct mks_params *P, uint64_t r0, uint64_t r1)
+{
+    return mks_fastq_offset(P, r1) - mks_fastq_offset(P, r0);
+}
+extern "C" uint64_t mk_synth_fasta_bytes(const struct mks_params *P, uint32_t s) { return mks_fasta_size(P, s); }
+extern "C" void mk_synth_shuf_perm(uint64_t seed, int subk, int32_t *perm) { mks_make_shuf_perm(seed, subk, perm); }
+extern "C" int32_t mk_synth_shuf_id(uint64_t seed) { return mks_shuf_id(seed); }

@@ -1,0 +1,101 @@
+"""Multi-GPU plumbing of the sketching path: one process per GPU, reads sharded
+by contiguous record ranges, one exchange step.
+
+Each rank reduces its shard to runs (code, first global position, count) sorted by code
+(mk_fastq_partial_device).  The code space [0, 2^code_bits) is cut into world_size equal ranges;
+a variable-size all-to-all (torch.distributed over NCCL/NVLink on GPUs, gloo in the CPU tests)
+delivers every run to the rank that owns its range, which merges them (sum of counts saturating
+at 65535, minimum first position).  The merged ranges are sent to rank 0, which reproduces the
+reference's hash-slot order (that needs all codes of a component in one table).
+
+torch is plumbing here: device memory views, the process group, the collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _CudaView:
+    """Zero-copy view of library-owned device memory through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def device_tensor(ptr: int, n: int, dtype: torch.dtype, device) -> torch.Tensor:
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=dtype, device=device)
+    typestr = {torch.int64: "<i8", torch.int32: "<i4"}[dtype]
+    return torch.as_tensor(_CudaView(ptr, n, typestr), device=device)
+
+
+def code_range_edges(world: int, code_bits: int) -> torch.Tensor:
+    return torch.tensor([(i << code_bits) // world for i in range(world + 1)], dtype=torch.int64)
+
+
+def split_sizes_by_code_range(codes: torch.Tensor, world: int, code_bits: int) -> list:
+    """codes: sorted int64 tensor (codes < 2^63).  Number of runs falling into each rank's range."""
+    edges = code_range_edges(world, code_bits).to(codes.device)
+    cut = torch.searchsorted(codes, edges)
+    return (cut[1:] - cut[:-1]).tolist()
+
+
+def all_to_all_runs(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tensor, send_sizes: list, group=None):
+    """Variable-size all-to-all of three parallel arrays; returns the received (code, pos, cnt)."""
+    world = dist.get_world_size(group)
+    dev = code.device
+    send = torch.tensor(send_sizes, dtype=torch.int64, device=dev)
+    recv = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send, group=group)
+    recv_sizes = recv.tolist()
+    n = int(sum(recv_sizes))
+    out = []
+    for t in (code, pos, cnt):
+        o = torch.empty(n, dtype=t.dtype, device=dev)
+        dist.all_to_all_single(o, t.contiguous(), output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
+                               group=group)
+        out.append(o)
+    return out[0], out[1], out[2]
+
+
+def merge_runs_reference(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tensor):
+    """Host/torch statement of the merge rule (used by the CPU tests and as documentation of
+    mk_runs_merge_device): per code, counts add up and saturate at 65535, first position is the
+    minimum.  Returns arrays sorted by code."""
+    if code.numel() == 0:
+        return code, pos, cnt
+    order = torch.argsort(code, stable=True)
+    c, p, k = code[order], pos[order], cnt[order].to(torch.int64)
+    uniq, inv = torch.unique_consecutive(c, return_inverse=True)
+    ksum = torch.zeros(uniq.numel(), dtype=torch.int64, device=c.device).scatter_add_(0, inv, k)
+    pmin = torch.full((uniq.numel(),), torch.iinfo(torch.int64).max, dtype=torch.int64, device=c.device)
+    pmin = pmin.scatter_reduce(0, inv, p, reduce="amin")
+    return uniq, pmin, torch.clamp(ksum, max=65535).to(cnt.dtype)
+
+
+def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_last: bool, group=None):
+    """The whole multi-GPU step for this rank's shard.  Returns the final Sketch on rank 0 (None
+    elsewhere).  `sk` is this rank's Sketcher; d_text its shard in device memory."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev = torch.device("cuda", sk.info.device)
+    runs = sk.fastq_partial_device(d_text, nbytes, pos_base, line_base, is_last)
+    n = int(runs.n)
+    code = device_tensor(runs.d_code, n, torch.int64, dev)
+    pos = device_tensor(runs.d_firstpos, n, torch.int64, dev)
+    cnt = device_tensor(runs.d_count, n, torch.int32, dev)
+    sizes = split_sizes_by_code_range(code, world, sk.info.code_bits)
+    rc, rp, rk = all_to_all_runs(code, pos, cnt, sizes, group)
+    torch.cuda.current_stream(dev).synchronize()
+    merged = sk.runs_merge_device(rc, rp, rk, int(rc.numel()))
+    m = int(merged.n)
+    mc = device_tensor(merged.d_code, m, torch.int64, dev)
+    mp = device_tensor(merged.d_firstpos, m, torch.int64, dev)
+    mk = device_tensor(merged.d_count, m, torch.int32, dev)
+    to_root = [m] + [0] * (world - 1)
+    gc, gp, gk = all_to_all_runs(mc, mp, mk, to_root, group)
+    torch.cuda.current_stream(dev).synchronize()
+    if rank != 0:
+        return None
+    return sk.runs_finalize_device(gc, gp, gk, int(gc.numel()))

@@ -1,0 +1,112 @@
+"""CPU: host-side mirror of the reference's formats and reporting (no GPU compute)."""
+import numpy as np
+import pytest
+
+
+def test_generators_agree(oracle, lib_built):
+    """Product generator helpers == oracle generator (same header, two libraries)."""
+    a = lib_built.synth_spec(42, 100, 1_000_000)
+    b = oracle.synth(42, 100, 1_000_000)
+    assert bytes(a.P) == bytes(b.P) and np.array_equal(a.cdf32, b.cdf32) and np.array_equal(a.species, b.species)
+    assert a.fastq_bytes(95, 10250) == b.fastq(95, 10250).size
+    assert a.fasta_bytes(7) == b.fasta(7).size
+    sid, perm = lib_built.make_shuf(77, 5)
+    sid2, perm2 = oracle.make_shuf(77, 11, 5, 2)
+    assert sid == sid2 and np.array_equal(perm, perm2)
+    assert np.array_equal(np.sort(perm), np.arange(1 << 20))
+
+
+def test_fastq_text_shape(oracle):
+    S = oracle.synth(3, 10, 100_000)
+    t = bytes(S.fastq(8, 12))
+    lines = t.split(b"\n")
+    assert lines[0] == b"@r8" and lines[8] == b"@r10" and lines[2] == b"+" and lines[3] == b"I" * 150
+    assert all(len(lines[i]) == 150 for i in (1, 5, 9, 13)) and t.endswith(b"\n")
+
+
+def test_shuf_file_round_trip(lib_built, tmp_path):
+    sid, perm = lib_built.make_shuf(5, 4)
+    p = tmp_path / "x.shuf"
+    lib_built.write_shuf(str(p), sid, 9, 4, 1, perm)
+    assert p.stat().st_size == 16 + 4 * (1 << 16)
+    sid2, k, subk, L, perm2 = lib_built.read_shuf(str(p))
+    assert (sid2, k, subk, L) == (sid, 9, 4, 1) and np.array_equal(perm, perm2)
+
+
+def test_sketch_dir_round_trip(lib_built, oracle, tmp_path):
+    """write_sketch_dir() produces what run_stageI() leaves on disk; the oracle-side reader (which
+    parses the reference's own directories in make_golden.py) reads it back."""
+    info = lib_built.MkInfo()
+    info.k, info.drlevel, info.component_num = 11, 2, 16
+    rng = np.random.default_rng(1)
+    sk = []
+    for _ in range(3):
+        codes = [rng.integers(0, 1 << 32, size=int(rng.integers(0, 50)), dtype=np.uint32) for _ in range(16)]
+        counts = [rng.integers(1, 65535, size=c.size, dtype=np.uint16) for c in codes]
+        sk.append(lib_built.Sketch(codes, counts))
+    names = ["a.fq", "dir/b.fastq", "c" * 300]
+    d = str(tmp_path / "sk")
+    lib_built.write_sketch_dir(d, 0x12345678, info, names, sk, koc=True)
+    sd = oracle.read_sketch_dir(d)
+    assert (sd.shuf_id, sd.koc, sd.kmerlen, sd.dim_rd_len, sd.comp_num, sd.infile_num) == (0x12345678, True, 22, 4, 16, 3)
+    assert sd.all_ctx_ct == sum(s.n_total for s in sk) and list(sd.ctx_ct) == [s.n_total for s in sk]
+    assert sd.names[:2] == names[:2] and sd.names[2] == "c" * 255
+    for c in range(16):
+        assert np.array_equal(sd.combco[c], np.concatenate([s.codes[c] for s in sk]))
+        assert np.array_equal(sd.abund[c], np.concatenate([s.counts[c] for s in sk]))
+        assert list(sd.index[c]) == [0] + list(np.cumsum([s.codes[c].size for s in sk]))
+    hdr, names2, combco, index, abund = lib_built.read_sketch_dir(d)
+    assert hdr["comp_num"] == 16 and names2 == sd.names and np.array_equal(combco[3], sd.combco[3])
+
+
+def _stats_numpy(lists):
+    """Restatement of command_composite.c:598-613 on plain lists (what mk_composite_stats computes)."""
+    out = np.zeros(len(lists), dtype=[("n", "<i4"), ("sum", "<i4"), ("lastsum", "<i4"), ("lastn", "<i4"),
+                                      ("median", "<i4"), ("max", "<i4")])
+    for s, v in enumerate(lists):
+        a = [len(v)] + sorted(int(x) for x in v)
+        n = len(v)
+        out[s]["n"] = n
+        out[s]["sum"] = sum(a[1:])
+        j, ls, ln = int(n * 0.98), 0, 0
+        while j <= n * 0.99:
+            ls += a[j]; ln += 1; j += 1
+        out[s]["lastsum"], out[s]["lastn"] = ls, ln
+        out[s]["median"] = a[n // 2] if n else 0
+        out[s]["max"] = a[n] if n else 0
+    return out
+
+
+def test_composite_tsv_matches_reference_printf(oracle, lib_built):
+    rng = np.random.default_rng(7)
+    S = 60
+    sizes = rng.integers(0, 400, size=S)
+    sizes[:5] = [0, 5, 6, 6, 1]                       # MIN_KM_S boundary and ties
+    ref_index = np.zeros(S + 1, dtype=np.uint64)
+    ref_index[1:] = np.cumsum(sizes)
+    ref_codes = rng.permutation(int(ref_index[-1]) * 3)[: int(ref_index[-1])].astype(np.uint32)
+    hit = rng.random(ref_codes.size) < 0.8
+    hit[: int(ref_index[5])] = True
+    qry_codes = np.concatenate([ref_codes[hit], np.arange(10**6, 10**6 + 500, dtype=np.uint32)])
+    qry_counts = rng.integers(1, 3000, size=qry_codes.size).astype(np.uint16)
+    perm = rng.permutation(qry_codes.size)
+    qry_codes, qry_counts = qry_codes[perm], qry_counts[perm]
+    names = ["%d_species%d" % (i + 1, i) for i in range(S)]
+    want = oracle.composite([(ref_codes, ref_index)], names, [(qry_codes, qry_counts)], "sample.fq")
+    lut = dict(zip(qry_codes.tolist(), qry_counts.tolist()))
+    lists = [[lut[c] for c in ref_codes[int(ref_index[s]):int(ref_index[s + 1])].tolist() if c in lut] for s in range(S)]
+    got = lib_built.composite_tsv("sample.fq", names, _stats_numpy(lists))
+    assert got == want and want.count("\n") > 40
+
+
+def test_markerdb_semantics(lib_built):
+    from helpers import markerdb_from_sketches
+    from metakssd_b200.workload import markerdb_from_species_sketches
+    rng = np.random.default_rng(3)
+    sk = [lib_built.Sketch([rng.choice(5000, size=400, replace=False).astype(np.uint32)], None) for _ in range(12)]
+    (codes, index), = markerdb_from_species_sketches(sk, 1)
+    c2, i2 = markerdb_from_sketches([s.codes[0] for s in sk])
+    assert np.array_equal(codes, c2) and np.array_equal(index, i2)
+    allc = np.concatenate([s.codes[0] for s in sk])
+    u, n = np.unique(allc, return_counts=True)
+    assert set(codes.tolist()) == set(u[n == 1].tolist())

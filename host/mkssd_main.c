@@ -1,0 +1,300 @@
+/*
+ * mkssd_main.c — C host program above the C ABI (include/mkssd_b200.h): the `dist`, `composite` and
+ * `shuffle` sub-commands of MetaKSSD restricted to the hot path, with the reference's flags and
+ * on-disk formats, calling the CUDA library instead of the CPU loops.
+ *
+ * Mirrors (behaviour, not code): cmd_dist/dist_dispatch/run_stageI (command_dist_wrapper.c:309,
+ * command_dist.c:49,341), cmd_composite/get_species_abundance (command_composite.c:145,446) and
+ * write_dim_shuffle_file (command_shuffle.c:164).  Written from scratch.
+ *
+ *   metakssd-b200 shuffle -k 11 -s 6 -l 3 -o L3K11 [--seed N]
+ *   metakssd-b200 dist -L L3K11.shuf -A -o sketch reads.fq [more inputs ...]
+ *   metakssd-b200 dist -L L3K11.shuf -o gsk sp1.fasta sp2.fasta ...
+ *   metakssd-b200 composite -r markerdb -q sketch > species_coverage.tsv
+ *
+ * Differences from the reference, all outside the sketch content: input files keep their command
+ * line order (the reference shuffles them with srand(time)); -p is accepted and ignored (the GPU
+ * library is driven from one host thread).
+ */
+#define _GNU_SOURCE
+#include <errno.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <sys/stat.h>
+#include <time.h>
+#include "mkssd_b200.h"
+
+#define PATHLEN 256
+#define MIN_KM_S 6
+
+typedef struct {           /* co_dstat_t, global_basic.h:116-126 */
+    unsigned int shuf_id;
+    bool koc;
+    int kmerlen, dim_rd_len, comp_num, infile_num;
+    unsigned long long all_ctx_ct;
+} co_dstat_t;
+
+static void die(const char *what, const char *arg)
+{
+    fprintf(stderr, "metakssd-b200: %s%s%s\n", what, arg ? ": " : "", arg ? arg : "");
+    exit(1);
+}
+static void ck(mk_ctx *ctx, int rc, const char *where)
+{
+    if (rc == MK_OK) return;
+    fprintf(stderr, "metakssd-b200: %s: %s (%s)\n", where, mk_strerror(rc), ctx ? mk_last_error(ctx) : "");
+    exit(rc == MK_ERR_CROWDED ? 2 : 1);
+}
+static bool has_ext(const char *path, const char *const *exts)
+{
+    char buf[1024];
+    snprintf(buf, sizeof buf, "%s", path);
+    size_t n = strlen(buf);
+    if (n > 3 && !strcmp(buf + n - 3, ".gz")) buf[n - 3] = 0;
+    else if (n > 4 && !strcmp(buf + n - 4, ".bz2")) buf[n - 4] = 0;
+    n = strlen(buf);
+    for (; *exts; exts++) {
+        size_t m = strlen(*exts);
+        if (n > m && buf[n - m - 1] == '.' && !strcasecmp(buf + n - m, *exts)) return true;
+    }
+    return false;
+}
+static void *slurp(const char *path, size_t *bytes)
+{
+    FILE *f = fopen(path, "rb");
+    if (!f) die("cannot open", path);
+    struct stat st;
+    if (stat(path, &st)) die("cannot stat", path);
+    void *p = malloc(st.st_size ? st.st_size : 1);
+    if (!p || fread(p, 1, st.st_size, f) != (size_t)st.st_size) die("cannot read", path);
+    fclose(f);
+    *bytes = st.st_size;
+    return p;
+}
+
+/* ---- shuffle ------------------------------------------------------------------------------ */
+static int cmd_shuffle(int argc, char **argv)
+{
+    int k = 8, s = 5, l = 2;
+    const char *out = "default";
+    uint64_t seed = (uint64_t)time(NULL);
+    for (int i = 0; i < argc; i++) {
+        if (!strcmp(argv[i], "-k") && i + 1 < argc) k = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-s") && i + 1 < argc) s = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-l") && i + 1 < argc) l = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-o") && i + 1 < argc) out = argv[++i];
+        else if (!strcmp(argv[i], "--seed") && i + 1 < argc) seed = strtoull(argv[++i], NULL, 0);
+    }
+    if (k < s) die("half-context length must not be shorter than the half-subcontext length", NULL);
+    if (s >= 8) die("subk should be smaller than 8", NULL);
+    size_t n = (size_t)1 << (4 * s);
+    int32_t *perm = malloc(n * sizeof *perm);
+    if (!perm) die("out of memory", NULL);
+    mk_synth_shuf_perm(seed, s, perm);
+    int hdr[4] = {mk_synth_shuf_id(seed), k, s, l};
+    char path[PATHLEN + 8];
+    snprintf(path, sizeof path, "%s.shuf", out);
+    FILE *f = fopen(path, "wb");
+    if (!f) die("cannot create", path);
+    fwrite(hdr, sizeof hdr, 1, f);
+    fwrite(perm, sizeof *perm, n, f);
+    fclose(f);
+    printf("kssd shuffle: shuf_id=%d, k = %d, halfCtxLen = %d, level= %d\n", hdr[0], k, s, l);
+    free(perm);
+    return 0;
+}
+
+/* ---- dist ------------------------------------------------------------------------------------ */
+static int cmd_dist(int argc, char **argv)
+{
+    const char *shuf = NULL, *outdir = "./", *pipecmd = "";
+    bool abundance = false;
+    char **inputs = malloc(sizeof(char *) * (size_t)(argc + 1));
+    int n_in = 0;
+    for (int i = 0; i < argc; i++) {
+        if (!strcmp(argv[i], "-L") && i + 1 < argc) shuf = argv[++i];
+        else if (!strcmp(argv[i], "-o") && i + 1 < argc) outdir = argv[++i];
+        else if (!strcmp(argv[i], "-p") && i + 1 < argc) ++i;
+        else if (!strcmp(argv[i], "-P") && i + 1 < argc) pipecmd = argv[++i];
+        else if (!strcmp(argv[i], "-A")) abundance = true;
+        else if (argv[i][0] == '-') die("option not on the hot path", argv[i]);
+        else inputs[n_in++] = argv[i];
+    }
+    if (!shuf) die("-L <file.shuf> is required", NULL);
+    if (!n_in) die("no input sequence files", NULL);
+    size_t sb;
+    int *sh = slurp(shuf, &sb);
+    int shuf_id = sh[0], k = sh[1], subk = sh[2], drl = sh[3];
+    if (sb != 16 + ((size_t)4 << (4 * subk))) die("malformed .shuf file", shuf);
+
+    mk_ctx *ctx = NULL;
+    ck(NULL, mk_ctx_create(&ctx, sh + 4, k, subk, drl, 0), "mk_ctx_create");
+    mk_info info;
+    mk_ctx_info(ctx, &info);
+    printf("rand_id=%d\thalf_ctx_len=%d\thashsize=%u\thashlimit=%u\n", shuf_id, k, info.hashsize, info.hashlimit);
+    mkdir(outdir, 0777);
+
+    static const char *const fq_ext[] = {"fq", "fastq", NULL};
+    mk_sketch *sk = calloc((size_t)n_in, sizeof *sk);
+    for (int i = 0; i < n_in; i++) {
+        bool fq = has_ext(inputs[i], fq_ext) || pipecmd[0];
+        if (fq && abundance) {
+            printf("running mt_shortreads2koc()\n");
+            ck(ctx, mk_fastq_koc_file(ctx, inputs[i], pipecmd, &sk[i]), inputs[i]);
+        } else if (fq) {
+            die("FASTQ without -A is outside the accelerated path", inputs[i]);
+        } else {
+            if (abundance) {
+                abundance = false;
+                printf("Warning: close abundance mode (-A) since non-fastq file input.\n");
+            }
+            ck(ctx, mk_fasta_co_file(ctx, inputs[i], pipecmd, &sk[i]), inputs[i]);
+        }
+        printf("%d/%d decomposing %s\r", i + 1, n_in, inputs[i]);
+    }
+    printf("\n");
+    /* combco.<c>, combco.<c>.a, combco.index.<c>  (command_dist.c:408-470) */
+    unsigned long long all_ct = 0;
+    char path[PATHLEN * 2];
+    for (int c = 0; c < info.component_num; c++) {
+        snprintf(path, sizeof path, "%s/combco.%d", outdir, c);
+        FILE *fc = fopen(path, "wb");
+        snprintf(path, sizeof path, "%s/combco.index.%d", outdir, c);
+        FILE *fi = fopen(path, "wb");
+        FILE *fa = NULL;
+        if (abundance) {
+            snprintf(path, sizeof path, "%s/combco.%d.a", outdir, c);
+            fa = fopen(path, "wb");
+        }
+        if (!fc || !fi || (abundance && !fa)) die("cannot write into", outdir);
+        size_t off = 0;
+        fwrite(&off, sizeof off, 1, fi);
+        for (int i = 0; i < n_in; i++) {
+            fwrite(sk[i].codes[c], 4, sk[i].n[c], fc);
+            if (fa) fwrite(sk[i].counts[c], 2, sk[i].n[c], fa);
+            off += sk[i].n[c];
+            fwrite(&off, sizeof off, 1, fi);
+        }
+        fclose(fc); fclose(fi);
+        if (fa) fclose(fa);
+    }
+    /* cofiles.stat (command_dist.c:477-500) */
+    co_dstat_t st;
+    memset(&st, 0, sizeof st);
+    st.shuf_id = (unsigned)shuf_id; st.koc = abundance; st.kmerlen = 2 * k; st.dim_rd_len = 2 * drl;
+    st.comp_num = info.component_num; st.infile_num = n_in;
+    for (int i = 0; i < n_in; i++) all_ct += sk[i].n_total;
+    st.all_ctx_ct = all_ct;
+    snprintf(path, sizeof path, "%s/cofiles.stat", outdir);
+    FILE *fs = fopen(path, "wb");
+    if (!fs) die("cannot write", path);
+    fwrite(&st, sizeof st, 1, fs);
+    for (int i = 0; i < n_in; i++) { unsigned int ct = (unsigned)sk[i].n_total; fwrite(&ct, 4, 1, fs); }
+    for (int i = 0; i < n_in; i++) {
+        char name[PATHLEN];
+        memset(name, 0, sizeof name);
+        snprintf(name, sizeof name, "%s", inputs[i]);
+        fwrite(name, PATHLEN, 1, fs);
+    }
+    fclose(fs);
+    for (int i = 0; i < n_in; i++) mk_sketch_free(&sk[i]);
+    mk_ctx_destroy(ctx);
+    free(sk); free(sh); free(inputs);
+    return 0;
+}
+
+/* ---- composite ---------------------------------------------------------------------------- */
+static const mk_species_stat *g_stats;
+static int by_hits_desc(const void *a, const void *b) { return g_stats[*(const int *)b].n - g_stats[*(const int *)a].n; }
+
+typedef struct { co_dstat_t st; char (*names)[PATHLEN]; } sketch_dir;
+static sketch_dir read_stat(const char *dir)
+{
+    char path[PATHLEN * 2];
+    snprintf(path, sizeof path, "%s/cofiles.stat", dir);
+    size_t n;
+    char *raw = slurp(path, &n);
+    sketch_dir d;
+    memcpy(&d.st, raw, sizeof d.st);
+    if (n < sizeof d.st + (size_t)d.st.infile_num * (4 + PATHLEN)) die("malformed cofiles.stat under", dir);
+    d.names = malloc((size_t)d.st.infile_num * PATHLEN);
+    memcpy(d.names, raw + sizeof d.st + (size_t)d.st.infile_num * 4, (size_t)d.st.infile_num * PATHLEN);
+    free(raw);
+    return d;
+}
+
+static int cmd_composite(int argc, char **argv)
+{
+    const char *refdir = NULL, *qrydir = NULL;
+    for (int i = 0; i < argc; i++) {
+        if (!strcmp(argv[i], "-r") && i + 1 < argc) refdir = argv[++i];
+        else if (!strcmp(argv[i], "-q") && i + 1 < argc) qrydir = argv[++i];
+        else if (!strcmp(argv[i], "-p") && i + 1 < argc) ++i;
+        else die("option not on the hot path", argv[i]);
+    }
+    if (!refdir || !qrydir || !strcmp(refdir, qrydir)) die("refdir or qrydir is not initialized", NULL);
+    sketch_dir R = read_stat(refdir), Q = read_stat(qrydir);
+    if (!Q.st.koc) die("get_species_abundance(): query has not abundance", NULL);
+    if (Q.st.shuf_id != R.st.shuf_id)
+        printf("get_species_abundance(): qry shuf_id %u not match ref shuf_id: %u\n", Q.st.shuf_id, R.st.shuf_id);
+    /* the library needs the sketch geometry only for its context; composite itself is geometry free */
+    int k = R.st.kmerlen / 2, drl = R.st.dim_rd_len / 2;
+    int subk = drl + 3 > k ? k : drl + 3;
+    size_t np = (size_t)1 << (4 * subk);
+    int32_t *perm = malloc(np * 4);
+    for (size_t i = 0; i < np; i++) perm[i] = (int32_t)i;
+    mk_ctx *ctx = NULL;
+    ck(NULL, mk_ctx_create(&ctx, perm, k, subk, drl, 0), "mk_ctx_create");
+    free(perm);
+    int S = R.st.infile_num;
+    mk_species_stat *stats = malloc(sizeof *stats * (size_t)S);
+    int *order = malloc(sizeof(int) * (size_t)S);
+    char path[PATHLEN * 2];
+    for (int qn = 0; qn < Q.st.infile_num; qn++) {
+        ck(ctx, mk_composite_begin(ctx, S), "mk_composite_begin");
+        for (int c = 0; c < R.st.comp_num; c++) {
+            size_t b;
+            snprintf(path, sizeof path, "%s/combco.%d", refdir, c);
+            uint32_t *rc = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.index.%d", refdir, c);
+            uint64_t *ri = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.%d", qrydir, c);
+            uint32_t *qc = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.index.%d", qrydir, c);
+            uint64_t *qi = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.%d.a", qrydir, c);
+            uint16_t *qa = slurp(path, &b);
+            ck(ctx, mk_composite_component(ctx, rc, ri, S, qc, qa, qi[qn], qi[qn + 1]), "mk_composite_component");
+            free(rc); free(ri); free(qc); free(qi); free(qa);
+        }
+        ck(ctx, mk_composite_stats(ctx, stats), "mk_composite_stats");
+        for (int i = 0; i < S; i++) order[i] = i;
+        g_stats = stats;
+        qsort(order, (size_t)S, sizeof(int), by_hits_desc);         /* command_composite.c:584 */
+        for (int i = 0; i < S; i++) {
+            const mk_species_stat *s = &stats[order[i]];
+            if (s->n < MIN_KM_S) break;
+            printf("%s\t%s\t%d\t%f\t%f\t%d\t%d\n", Q.names[qn], R.names[order[i]], s->n, (float)s->sum / s->n,
+                   (float)s->lastsum / s->lastn, s->median, s->max);    /* command_composite.c:624 */
+        }
+    }
+    mk_ctx_destroy(ctx);
+    return 0;
+}
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) {
+        fprintf(stderr, "usage: %s <shuffle|dist|composite> [options] [arguments]\n", argv[0]);
+        return 1;
+    }
+    if (!strcmp(argv[1], "shuffle")) return cmd_shuffle(argc - 2, argv + 2);
+    if (!strcmp(argv[1], "dist")) return cmd_dist(argc - 2, argv + 2);
+    if (!strcmp(argv[1], "composite")) return cmd_composite(argc - 2, argv + 2);
+    die("sub-command outside the accelerated path", argv[1]);
+    return 1;
+}

@@ -1,0 +1,61 @@
+"""GPU (needs >= 2 devices, skipped otherwise): the sharded path — per-rank partial sketches, NCCL
+all-to-all by code range, merge, slot-order reconstruction on rank 0 — must give exactly the sketch
+of the concatenated input on one GPU."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = textwrap.dedent('''
+    import os, sys
+    sys.path.insert(0, %r)
+    import numpy as np, torch, torch.distributed as dist
+    import metakssd_b200 as M
+    from metakssd_b200 import distributed as D
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    k, subk, L = 11, 6, 3
+    sid, perm = M.make_shuf(77, subk)
+    spec = M.synth_spec(5, 50, 300_000, 150)
+    per = 200_000
+    sk = M.Sketcher(perm, k, subk, L, device=local)
+    r0, r1 = rank * per, (rank + 1) * per
+    nb = spec.fastq_bytes(r0, r1)
+    d = torch.empty(nb + 256, dtype=torch.uint8, device=dev)
+    sk.synth_fastq_device(spec.P, spec.cdf32, spec.species, r0, r1, d, d.numel())
+    got = D.sketch_sharded(sk, d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1)
+    if rank == 0:
+        nball = spec.fastq_bytes(0, world * per)
+        full = torch.empty(nball + 256, dtype=torch.uint8, device=dev)
+        sk.synth_fastq_device(spec.P, spec.cdf32, spec.species, 0, world * per, full, full.numel())
+        want = sk.fastq_koc_device(full, nball)
+        assert got.n_total == want.n_total > 1000, (got.n_total, want.n_total)
+        for c in range(len(want.codes)):
+            assert np.array_equal(got.codes[c], want.codes[c]), "codes/order differ"
+            assert np.array_equal(got.counts[c], want.counts[c]), "counts differ"
+        print("MULTI_OK", want.n_total)
+    dist.barrier()
+    dist.destroy_process_group()
+''')
+
+
+def test_sharded_equals_single_gpu(tmp_path, lib_built):
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else 4
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", str(script)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "MULTI_OK" in r.stdout

@@ -201,14 +201,72 @@ __device__ __forceinline__ bool verify_kmer(const uint8_t *t, const KParams &kp,
     return true;
 }
 
+// The probe is bound by the integer ALU pipe (shifts, logic); the FMA pipe, which also executes
+// IMAD / IMAD.HI, is mostly idle.  Right shifts by a compile-time amount are therefore written as
+// "high half of a multiply by 2^(32-s)" so that ptxas places them on the FMA pipe.
+#ifndef MK_ALU_SHIFTS
+template <int SH>
+__device__ __forceinline__ u32 shr_fma(u32 x)
+{
+    if (SH == 0) return x;
+    return __umulhi(x, 1u << ((32 - SH) & 31));
+}
+#else
+template <int SH>
+__device__ __forceinline__ u32 shr_fma(u32 x) { return x >> SH; }
+#endif
+
 // 16 ASCII bases -> 32 bits, base i at bits [2i, 2i+2) (garbage for non-ACGT bytes, by design)
 __device__ __forceinline__ u32 pack16(uint4 v)
 {
-    u32 x0 = (((v.x >> 1) ^ (v.x >> 2)) & 0x03030303u) * 0x01041040u;
-    u32 x1 = (((v.y >> 1) ^ (v.y >> 2)) & 0x03030303u) * 0x01041040u;
-    u32 x2 = (((v.z >> 1) ^ (v.z >> 2)) & 0x03030303u) * 0x01041040u;
-    u32 x3 = (((v.w >> 1) ^ (v.w >> 2)) & 0x03030303u) * 0x01041040u;
-    return (x0 >> 24) | ((x1 >> 16) & 0x0000FF00u) | ((x2 >> 8) & 0x00FF0000u) | (x3 & 0xFF000000u);
+    u32 x0 = ((shr_fma<1>(v.x) ^ shr_fma<2>(v.x)) & 0x03030303u) * 0x01041040u;
+    u32 x1 = ((shr_fma<1>(v.y) ^ shr_fma<2>(v.y)) & 0x03030303u) * 0x01041040u;
+    u32 x2 = ((shr_fma<1>(v.z) ^ shr_fma<2>(v.z)) & 0x03030303u) * 0x01041040u;
+    u32 x3 = ((shr_fma<1>(v.w) ^ shr_fma<2>(v.w)) & 0x03030303u) * 0x01041040u;
+    return __byte_perm(__byte_perm(x0, x1, 0x0073), __byte_perm(x2, x3, 0x7300), 0x7610);
+}
+
+// window extraction for position J: 32 bits of the packed bases starting at bit offset O; only
+// bits [0, NEED) of the result are used, which lets single-word cases run on the FMA pipe.
+template <int O, int NEED>
+__device__ __forceinline__ u32 take_bits(const u32 (&A)[4])
+{
+    constexpr int W = O >> 5, SH = O & 31;
+    if (SH + NEED <= 32) return shr_fma<SH>(A[W]);
+    return __funnelshift_r(A[W], A[W + 1], SH);
+}
+
+template <int ROTOFF, u32 WORDMASK, int J>
+__device__ __forceinline__ void probe_one(const u32 (&A)[4], const u32 *bm, u32 &hits)
+{
+    constexpr int NEEDV = (WORDMASK == 0x1FFFCu) ? 17 : (WORDMASK == 0x1FFCu ? 13 : 9);
+    u32 v = take_bits<2 * J, NEEDV>(A);
+    u32 r = take_bits<2 * J + ROTOFF, 5>(A);
+    u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + (v & WORDMASK));
+    u32 rot = __funnelshift_l(word, word, r);
+    hits = __funnelshift_l(rot, hits, 1);
+    if constexpr (J < 31) probe_one<ROTOFF, WORDMASK, J + 1>(A, bm, hits);
+}
+
+// Packed bases of one block: A[0..2], position j's inner window starting at bit 2j (+2*spare).
+template <int PREW>
+__device__ __forceinline__ void load_block(const uint8_t *blk, int shift_s, u32 (&A)[4])
+{
+    u32 W[PREW + 3];
+    const uint4 *q = reinterpret_cast<const uint4 *>(blk - 16 * PREW);
+    const bool rot = (threadIdx.x >> 2) & 1;
+    if (PREW == 1) {
+        u32 w0 = pack16(q[rot ? 1 : 0]), w1 = pack16(q[rot ? 2 : 1]), w2 = pack16(q[rot ? 0 : 2]);
+        W[0] = rot ? w2 : w0; W[1] = rot ? w0 : w1; W[2] = rot ? w1 : w2;
+    } else {
+        u32 w0 = pack16(q[rot ? 2 : 0]), w1 = pack16(q[rot ? 3 : 1]), w2 = pack16(q[rot ? 0 : 2]), w3 = pack16(q[rot ? 1 : 3]);
+        W[0] = rot ? w2 : w0; W[1] = rot ? w3 : w1; W[2] = rot ? w0 : w2; W[PREW + 1] = rot ? w1 : w3;
+    }
+    W[PREW + 2] = 0;
+    A[0] = __funnelshift_r(W[0], W[1], shift_s);
+    A[1] = __funnelshift_r(W[1], W[2], shift_s);
+    A[2] = __funnelshift_r(W[2], W[3], shift_s);
+    A[3] = 0;
 }
 
 // Probe the 32 k-mer end positions of one aligned 32-byte block against the bitmap.
@@ -217,25 +275,9 @@ __device__ __forceinline__ u32 pack16(uint4 v)
 template <int ROTOFF, u32 WORDMASK, int PREW>
 __device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, int shift_s, u32 (&A)[4])
 {
-    u32 W[PREW + 3];
-    const uint4 *q = reinterpret_cast<const uint4 *>(blk - 16 * PREW);
-#pragma unroll
-    for (int i = 0; i < PREW + 2; i++) W[i] = pack16(q[i]);
-    W[PREW + 2] = 0;
-    A[0] = __funnelshift_r(W[0], W[1], shift_s);
-    A[1] = __funnelshift_r(W[1], W[2], shift_s);
-    A[2] = __funnelshift_r(W[2], W[3], shift_s);
-    A[3] = 0;
+    load_block<PREW>(blk, shift_s, A);
     u32 hits = 0;
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const int o = 2 * j, o2 = 2 * j + ROTOFF;
-        u32 v = __funnelshift_r(A[o >> 5], A[(o >> 5) + 1], o & 31);
-        u32 r = __funnelshift_r(A[o2 >> 5], A[(o2 >> 5) + 1], o2 & 31);
-        u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + (v & WORDMASK));
-        u32 rot = __funnelshift_l(word, word, r);
-        hits = __funnelshift_l(rot, hits, 1);
-    }
+    probe_one<ROTOFF, WORDMASK, 0>(A, bm, hits);
     return __brev(hits);
 }
 
@@ -302,7 +344,7 @@ struct StreamSmem {
     u32 scur[3];                 // scan-chunk cursor per stage
     u32 sdone[3];                // scanned chunks per stage
     u32 n_items[2];              // items per buffer
-    u32 icur, bdone, mcur;
+    u32 icur[2], pdone[2], mcur;    // item cursor / completed probe units per item buffer
     volatile u32 resolved;       // iteration stamp: line number of `next` is available
 };
 
@@ -325,7 +367,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
     if (tid == 0) {
         for (int s = 0; s < 3; s++) { mbar_init(&S.bar[s], 1); S.scur[s] = 0; S.sdone[s] = 0; S.tot[s] = 0; S.P[s] = 0; }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        S.n_items[0] = 0; S.n_items[1] = 0; S.icur = 0; S.bdone = 0; S.mcur = 0; S.resolved = 0;
+        S.n_items[0] = 0; S.n_items[1] = 0; S.icur[0] = S.icur[1] = 0; S.pdone[0] = S.pdone[1] = 0; S.mcur = 0; S.resolved = 0;
     }
     __syncthreads();
 
@@ -383,18 +425,28 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
             }
             u32 m0 = 0, m1 = 0;
             if (!RAW && off < TB) {
+                // lane l owns bytes [64 l, 64 l + 64) of the chunk: with a 64-byte lane stride the four
+                // 128-bit loads would be 4-way bank conflicted; lane l therefore starts at piece (l/2) % 4
+                // and the 16-bit piece masks are placed by piece index afterwards.
                 const uint4 *q = reinterpret_cast<const uint4 *>(tx + MK_HALO + off);
-                u32 w[16];
+                const u32 rot = (lane >> 1) & 3u;
 #pragma unroll
-                for (int k4 = 0; k4 < 4; k4++) { uint4 v = q[k4]; w[4 * k4] = v.x; w[4 * k4 + 1] = v.y; w[4 * k4 + 2] = v.z; w[4 * k4 + 3] = v.w; }
+                for (int k4 = 0; k4 < 4; k4++) {
+                    const u32 pc = (k4 + rot) & 3u;
+                    uint4 v = q[pc];
+                    u32 w[4] = {v.x, v.y, v.z, v.w};
+                    u32 m = 0;
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    // exact "byte == 0x0A": bit 7 of t7 is set iff the low 7 bits of (byte ^ 0x0A) are non-zero
-                    u32 t7 = ((w[j] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                    u32 f = ~(t7 | w[j]) & 0x80808080u;
-                    u32 nib = __umulhi(f, 0x02040810u);   // bits 7,15,23,31 -> bits 0..3 (junk above)
-                    if (j < 8) m0 = __funnelshift_r(m0, nib, 4);
-                    else       m1 = __funnelshift_r(m1, nib, 4);
+                    for (int j = 0; j < 4; j++) {
+                        // exact "byte == 0x0A": bit 7 of t7 is set iff the low 7 bits of (byte ^ 0x0A) are non-zero
+                        u32 t7 = ((w[j] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                        u32 f = ~(t7 | w[j]) & 0x80808080u;
+                        u32 nib = __umulhi(f, 0x02040810u);   // bits 7,15,23,31 -> bits 0..3 (junk above)
+                        m = __funnelshift_r(m, nib, 4);
+                    }
+                    m >>= 16;                                  // 16-bit newline mask of this piece
+                    m <<= (pc & 1u) * 16u;
+                    if (pc & 2u) m1 |= m; else m0 |= m;
                 }
             }
             if (!RAW) {
@@ -555,7 +607,11 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         uint8_t *tx = tbuf + stage * TBUF_STRIDE;
         const u64 T = (u64)cur * TB;
         const u32 n_items = S.n_items[buf];
-        if (tid == 0) S.mcur = 0;                          // nobody pulls M units before `resolved` is stamped
+        if (tid == 0) {                                    // next iteration's cursors; nobody touches them now
+            S.mcur = 0;                                    // (M units are not pulled before `resolved` is stamped)
+            S.icur[buf ^ 1] = 0;
+            S.pdone[buf ^ 1] = 0;
+        }
         const bool tr = A.trace && blockIdx.x == 0 && iter <= 64 && lane == 0;
         u64 *trp = A.trace + ((u64)(iter - 1) * NWARPS + wid) * 8;
         if (tr) { trp[0] = clock64(); trp[6] = n_items; trp[7] = cur; }
@@ -575,37 +631,41 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         }
         if (tr) trp[1] = clock64();
 
-        // ---- P units ---------------------------------------------------------------------------
-        for (;;) {
-            u32 base = 0;
-            if (lane == 0) base = atomicAdd(&S.icur, 32u);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (base >= n_items) break;
-            const u32 it = base + lane;
-            if (it < n_items) {
-                const u32 b = S.items[buf][it];
-                u32 Aw[4];
-                u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
-                hits &= S.posmask[buf][b];
-                while (hits) {
-                    u32 j = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
-                    emit_hit(A, T + 32 * b + j);
+        // ---- P units: pulled by every warp; warps 0 and 1 (warp 0 is busy with the look-back) take
+        //      scan and mask units first and only then whatever probe units are left -----------------
+        const u32 nP = (n_items + 31u) >> 5;
+        auto probe_units = [&]() {
+            for (;;) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&S.icur[buf], 32u);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (base >= n_items) break;
+                const u32 it = base + lane;
+                if (it < n_items) {
+                    const u32 b = S.items[buf][it];
+                    u32 Aw[4];
+                    u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
+                    hits &= S.posmask[buf][b];
+                    while (hits) {
+                        u32 j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
+                        emit_hit(A, T + 32 * b + j);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) {                           // the warp completing the last unit recycles the stage
+                    __threadfence_block();
+                    if (atomicAdd(&S.pdone[buf], 1u) == nP - 1) {
+                        S.n_items[buf] = 0;
+                        claim_and_load(stage);
+                    }
                 }
             }
-        }
+        };
+        if (nP == 0 && tid == 0) { S.n_items[buf] = 0; claim_and_load(stage); }
+        if (wid >= 2) probe_units();
         if (tr) trp[2] = clock64();
-        {   // last warp out recycles the stage of `cur`
-            u32 d = 0;
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); d = atomicAdd(&S.bdone, 1u); }
-            d = __shfl_sync(0xffffffffu, d, 0);
-            if (d == NWARPS - 1 && lane == 0) {
-                S.n_items[buf] = 0; S.icur = 0; S.bdone = 0;
-                claim_and_load(stage);
-            }
-        }
         // ---- S units of the tile two ahead -----------------------------------------------------
         {
             u32 par = st2 == 0 ? (uses0 & 1u) : (st2 == 1 ? (uses1 & 1u) : (uses2 & 1u));
@@ -622,6 +682,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
         __threadfence_block();
         mask_units(st1, buf ^ 1, false);
         if (tr) trp[5] = clock64();
+        if (wid < 2) probe_units();
         stage = st1;
         buf ^= 1;
     }

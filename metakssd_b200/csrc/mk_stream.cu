@@ -688,6 +688,362 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
     }
 }
 
+// ================================================================================================
+// k_stream_ws — warp-specialised, barrier-free variant of the same pipeline.
+//
+// The unit-pulling kernel above spends a large share of its issue slots on shared-memory atomics,
+// fetch loops and one block barrier per tile.  Here every warp has a fixed role and a plain loop;
+// tiles flow through a ring of WS_NS shared-memory stages and the roles hand a stage over with
+// mbarriers (arrive / try_wait.parity), never with __syncthreads:
+//
+//   loader   (1 lane)   waits until the probe warps released the stage, claims the next ticket,
+//                       starts its TMA                                           -> full[s]
+//   front    (NFW warps) scan their chunks of the tile for '\n'                    -> scanned[s]
+//                       then build the sequence-byte masks + item list of the tile
+//                       before (software pipelined, so that the resolver has a whole
+//                       scan phase to finish)                                       -> ready[s]
+//   resolver (1 warp)   publishes the tile's newline count, sums the counts published since
+//                       this CTA's previous tile (decoupled look-back)             -> resolved[s]
+//   probe    (NPW warps) probe a static, per-tile rotated share of the items        -> done[s]
+//
+// The k-th tile of a CTA always uses stage k % WS_NS, so every role derives stage and mbarrier
+// parity from its own loop counter.
+// ================================================================================================
+#define WS_NS 4
+#define WS_TILE 16384
+#define WS_BLK (WS_TILE / 32)
+#define WS_CHUNK (WS_TILE / 2048)
+#define WS_NSW 4   // scan warps
+#define WS_NMW 2   // mask warps
+#define WS_NFW (WS_NSW + WS_NMW)
+#define WS_NPW 10  // probe warps
+#define WS_THREADS (32 * (2 + WS_NFW + WS_NPW))
+#define WS_TBUF (MK_HALO + WS_TILE + 96)
+
+struct WsStage {
+    u32 nlm[WS_BLK];
+    u32 posmask[WS_BLK];
+    uint16_t exw[WS_BLK];
+    uint16_t items[WS_BLK];
+    u32 ctot[WS_CHUNK];
+    u32 cpre[WS_CHUNK];
+};
+struct WsSmem {
+    WsStage st[WS_NS];
+    u64 full[WS_NS], scanned[WS_NS], resolved[WS_NS], ready[WS_NS], done[WS_NS];
+    u64 P[WS_NS];
+    u32 tile[WS_NS], n_items[WS_NS], scnt[WS_NS], tot[WS_NS];
+};
+
+__device__ __forceinline__ void mbar_arrive(u64 *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int ROTOFF, u32 WORDMASK, int PREW, bool RAW>
+__global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_constant__ StreamArgs A)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    const u32 tid = threadIdx.x;
+    const u32 lane = tid & 31, wid = tid >> 5;
+    const u32 bm_bytes = (A.bitmap_bytes + 127u) & ~127u;
+    u32 *bm = reinterpret_cast<u32 *>(smem);
+    uint8_t *tbuf = smem + bm_bytes;
+    WsSmem &S = *reinterpret_cast<WsSmem *>(tbuf + WS_NS * WS_TBUF);
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
+        uint4 *dst = reinterpret_cast<uint4 *>(bm);
+        for (u32 i = tid; i < A.bitmap_bytes / 16; i += WS_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < WS_NS; s++) {
+            mbar_init(&S.full[s], 1);
+            mbar_init(&S.scanned[s], WS_NSW);
+            mbar_init(&S.resolved[s], 1);
+            mbar_init(&S.ready[s], WS_NMW);
+            mbar_init(&S.done[s], WS_NPW);
+            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.P[s] = 0; S.scnt[s] = 0; S.tot[s] = 0;
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();   // the only block-wide barrier of the kernel
+
+    const u32 TB = A.tile_bytes;
+    const u32 NBLK = TB / 32;
+    const u32 NCHUNK = (TB + 2047u) / 2048u;
+    const u32 NMUNIT = (NBLK + 63u) / 64u;
+    auto tile_len = [&](u32 t) -> u32 {
+        u64 rem = A.nbytes - (u64)t * TB;
+        return rem < TB ? (u32)rem : TB;
+    };
+    auto watchdog = [&](u32 site, u64 a, u64 b, u64 c, u64 d) {
+        if (atomicOr(A.flags, FLAG_WATCHDOG) & FLAG_WATCHDOG) return;
+        A.wd[0] = site; A.wd[1] = blockIdx.x; A.wd[2] = wid; A.wd[3] = a; A.wd[4] = b; A.wd[5] = c; A.wd[6] = d;
+        A.wd[7] = ((u64)S.tile[0] << 42) | ((u64)S.tile[1] << 21) | (u64)S.tile[2];
+    };
+    auto stamp = [&](u32 k, u32 slot) {      // development aid: clock64() stamps of CTA 0, first 48 tiles
+        if (A.trace && blockIdx.x == 0 && k < 48 && lane == 0) A.trace[((u64)k * 32 + wid) * 4 + slot] = clock64();
+    };
+    // wait with a watchdog; false = gave up (the role then leaves the kernel)
+    auto wait_on = [&](u64 *bar, u32 parity, u32 site, u32 k) -> bool {
+        if (mbar_wait(bar, parity)) return true;
+        if (lane == 0) watchdog(site, k, parity, wid, 0);
+        return false;
+    };
+
+    if (wid == 0) {
+        // ======================= loader =========================================================
+        if (lane == 0) {
+            for (u32 k = 0;; k++) {
+                const u32 s = k % WS_NS, v = k / WS_NS;
+                if (v > 0 && !wait_on(&S.done[s], (v - 1) & 1u, 10, k)) break;
+                stamp(k, 0);
+                S.n_items[s] = 0;
+                const u32 t = atomicAdd(A.tile_counter, 1u);
+                S.tile[s] = t;
+                if (t >= A.n_tiles) { mbar_arrive(&S.full[s]); break; }   // end marker for every role
+                const u32 tb = tile_len(t);
+                uint8_t *dst = tbuf + s * WS_TBUF;
+                const uint8_t *src = A.text + (u64)t * TB;
+                u32 bytes = tb;
+                if (t > 0) { src -= MK_HALO; bytes += MK_HALO; } else { dst += MK_HALO; }
+                bytes = (bytes + 15u) & ~15u;
+                fence_proxy_async();
+                mbar_expect_tx(&S.full[s], bytes);
+                tma_load_1d(dst, src, bytes, &S.full[s]);
+            }
+        }
+    } else if (wid == 1) {
+        // ======================= resolver =======================================================
+        long long prev_t = -1;
+        u64 prev_incl = 0;
+        const u64 VMASK = (1ull << 62) - 1;
+        for (u32 k = 0;; k++) {
+            const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
+            if (!wait_on(&S.full[s], par, 20, k)) break;
+            const u32 t = S.tile[s];
+            if (t >= A.n_tiles) break;
+            stamp(k, 0);
+            if (!wait_on(&S.scanned[s], par, 21, k)) break;
+            stamp(k, 1);
+            if (!RAW) {
+                const u32 total = S.tot[s];
+                // newlines before t = newlines through prev_t + counts of the tiles in between
+                u64 sum = 0;
+                bool ok = true;
+                for (long long i0 = prev_t + 1; i0 < (long long)t; i0 += 128) {
+                    u64 d[4];
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) {
+                        long long idx = i0 + 32 * k4 + (long long)lane;
+                        d[k4] = idx < (long long)t ? ld_volatile_u64(&A.tile_desc[idx]) : (1ull << 62);
+                    }
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) {
+                        long long idx = i0 + 32 * k4 + (long long)lane;
+                        for (u32 n = 0; (d[k4] >> 62) == 0; n++) {
+                            if (n > WD_LIMIT) { watchdog(22, t, (u64)idx, (u64)prev_t, k); ok = false; break; }
+                            __nanosleep(100);
+                            d[k4] = ld_volatile_u64(&A.tile_desc[idx]);
+                        }
+                        sum += d[k4] & VMASK;
+                    }
+                }
+                const u64 excl = prev_incl + warp_sum_u64(sum);
+                prev_t = (long long)t;
+                prev_incl = excl + total;
+                if (lane == 0) {
+                    S.P[s] = A.line_base + excl;
+                    if (t == A.n_tiles - 1) *A.total_newlines = A.line_base + excl + total;
+                }
+                if (!__all_sync(0xffffffffu, ok)) break;
+            }
+            stamp(k, 2);
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); mbar_arrive(&S.resolved[s]); }
+        }
+    } else if (wid < 2 + WS_NFW) {
+        // ======================= front end: scan warps and mask warps ==============================
+        const u32 fw = wid - 2;
+        auto scan = [&](u32 s, u32 t) {
+            WsStage &G = S.st[s];
+            uint8_t *tx = tbuf + s * WS_TBUF;
+            const u32 tb = tile_len(t);
+            for (u32 c = fw; c < NCHUNK; c += WS_NSW) {
+                const u32 off = c * 2048u + lane * 64u;        // my 64 bytes (two blocks)
+                if (t == 0 && c == 0 && lane < MK_HALO / 4) reinterpret_cast<u32 *>(tx)[lane] = 0;
+                if (off + 64u > tb && off < TB) {               // blank what lies outside the text
+                    u32 from = off > tb ? off : tb;
+                    for (u32 i = from; i < off + 64u; i++) tx[MK_HALO + i] = 0;
+                }
+                if (RAW) continue;
+                u32 m0 = 0, m1 = 0;
+                if (off < TB) {
+                    const uint4 *q = reinterpret_cast<const uint4 *>(tx + MK_HALO + off);
+                    const u32 rot = (lane >> 1) & 3u;           // conflict-free piece order (see k_stream)
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; k4++) {
+                        const u32 pc = (k4 + rot) & 3u;
+                        uint4 v = q[pc];
+                        u32 w[4] = {v.x, v.y, v.z, v.w};
+                        u32 m = 0;
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            u32 t7 = ((w[j] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                            u32 f = ~(t7 | w[j]) & 0x80808080u;            // 0x80 where the byte is '\n' (exact)
+                            m = __funnelshift_r(m, __umulhi(f, 0x02040810u), 4);
+                        }
+                        m >>= 16;
+                        m <<= (pc & 1u) * 16u;
+                        if (pc & 2u) m1 |= m; else m0 |= m;
+                    }
+                }
+                const u32 c0 = __popc(m0), cnt = c0 + __popc(m1);
+                u32 incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (u32)o) incl += x;
+                }
+                const u32 b0 = c * 64u + 2u * lane;
+                if (b0 < NBLK) { G.nlm[b0] = m0; G.exw[b0] = (uint16_t)(incl - cnt); }
+                if (b0 + 1 < NBLK) { G.nlm[b0 + 1] = m1; G.exw[b0 + 1] = (uint16_t)(incl - cnt + c0); }
+                if (lane == 31) G.ctot[c] = incl;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            // The front warp that finishes the tile's scan publishes its newline count right away:
+            // other CTAs' look-backs depend on it and must never wait behind our own look-back.
+            u32 old = 0;
+            if (lane == 0) { __threadfence_block(); old = atomicAdd(&S.scnt[s], 1u); }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            if (old == WS_NSW - 1 && !RAW) {
+                __threadfence_block();
+                u32 v = lane < NCHUNK ? G.ctot[lane] : 0;
+                u32 incl = v;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    u32 x = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= (u32)o) incl += x;
+                }
+                if (lane < NCHUNK) G.cpre[lane] = incl - v;
+                const u32 total = __shfl_sync(0xffffffffu, incl, 7);    // WS_CHUNK == 8 lanes carry values
+                if (lane == 0) {
+                    S.tot[s] = total;
+                    st_volatile_u64(&A.tile_desc[t], (1ull << 62) | (u64)total);
+                    if (total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
+                }
+            }
+            if (old == WS_NSW - 1 && lane == 0) S.scnt[s] = 0;
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); mbar_arrive(&S.scanned[s]); }
+        };
+        auto mask = [&](u32 s, u32 t) {
+            WsStage &G = S.st[s];
+            const u32 tb = tile_len(t);
+            const u32 P = RAW ? 0u : (u32)S.P[s];
+            for (u32 u = fw - WS_NSW; u < NMUNIT; u += WS_NMW) {
+                u32 pm[2];
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const u32 b = u * 64u + 32u * h + lane;
+                    pm[h] = 0;
+                    if (b < NBLK) {
+                        if (RAW) {
+                            u32 lo = 32 * b;
+                            pm[h] = lo >= tb ? 0u : (tb - lo >= 32 ? 0xffffffffu : ((1u << (tb - lo)) - 1u));
+                        } else {
+                            const u32 nl = G.nlm[b];
+                            const u32 s0 = (P + G.cpre[b >> 6] + G.exw[b]) & 3u;
+                            const u32 tgt = (1u - s0) & 3u;
+                            u32 p0 = 0, p1 = 0;
+                            if (nl) {
+                                p0 = prefix_xor(nl << 1);
+                                p1 = prefix_xor((nl & p0) << 1);
+                            }
+                            pm[h] = (p0 ^ ((tgt & 1u) ? 0u : ~0u)) & (p1 ^ ((tgt & 2u) ? 0u : ~0u)) & ~nl;
+                        }
+                        G.posmask[b] = pm[h];
+                    }
+                }
+                const u32 ma = __ballot_sync(0xffffffffu, pm[0] != 0);
+                const u32 mb = __ballot_sync(0xffffffffu, pm[1] != 0);
+                const u32 na = __popc(ma);
+                u32 base = 0;
+                if (lane == 0 && (ma | mb)) base = atomicAdd(&S.n_items[s], na + (u32)__popc(mb));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const u32 lt = (1u << lane) - 1u;
+                if (pm[0]) G.items[base + __popc(ma & lt)] = (uint16_t)(u * 64u + lane);
+                if (pm[1]) G.items[base + na + __popc(mb & lt)] = (uint16_t)(u * 64u + 32u + lane);
+            }
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); mbar_arrive(&S.ready[s]); }
+        };
+        if (fw < WS_NSW) {
+            // scan warps never wait for a look-back: newline counts of claimed tiles are published as
+            // soon as their text has landed, which is what keeps every CTA's resolver fast
+            for (u32 k = 0;; k++) {
+                const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
+                if (!wait_on(&S.full[s], par, 30, k)) break;
+                const u32 t = S.tile[s];
+                if (t >= A.n_tiles) break;
+                stamp(k, 0);
+                scan(s, t);
+                stamp(k, 1);
+            }
+        } else {
+            for (u32 k = 0;; k++) {
+                const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
+                if (!wait_on(&S.full[s], par, 32, k)) break;
+                const u32 t = S.tile[s];
+                if (t >= A.n_tiles) {                       // end marker: wake the probe warps and leave
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.ready[s]);
+                    break;
+                }
+                if (!wait_on(&S.resolved[s], par, 31, k)) break;
+                stamp(k, 2);
+                mask(s, t);
+                stamp(k, 3);
+            }
+        }
+    } else {
+        // ======================= probe ==========================================================
+        const u32 pw = wid - 2 - WS_NFW;
+        for (u32 k = 0;; k++) {
+            const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
+            stamp(k, 0);
+            if (!wait_on(&S.ready[s], par, 40, k)) break;
+            stamp(k, 1);
+            const u32 t = S.tile[s];
+            if (t >= A.n_tiles) break;
+            WsStage &G = S.st[s];
+            const uint8_t *tx = tbuf + s * WS_TBUF;
+            const u64 T = (u64)t * TB;
+            const u32 n = S.n_items[s];
+            for (u32 r = (pw + WS_NPW - (k % WS_NPW)) % WS_NPW; r * 32u < n; r += WS_NPW) {
+                const u32 it = r * 32u + lane;
+                if (it < n) {
+                    const u32 b = G.items[it];
+                    u32 Aw[4];
+                    u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
+                    hits &= G.posmask[b];
+                    while (hits) {
+                        u32 j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
+                        emit_hit(A, T + 32 * b + j);
+                    }
+                }
+            }
+            stamp(k, 2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.done[s]);
+        }
+    }
+}
+
 // ---- exact verification of the hit list -------------------------------------------------------
 // One thread per position that passed the shared-memory filter (true members of the pass set
 // plus ~0.025 % Bloom false positives): the TL bytes ending there must all be ACGT — hence lie
@@ -787,6 +1143,24 @@ extern "C" int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t 
 typedef void (*stream_kernel_t)(const StreamArgs);
 
 template <int ROTOFF, u32 WORDMASK>
+static stream_kernel_t pick2_ws(int prew, bool raw)
+{
+    if (prew == 1) return raw ? k_stream_ws<ROTOFF, WORDMASK, 1, true> : k_stream_ws<ROTOFF, WORDMASK, 1, false>;
+    return raw ? k_stream_ws<ROTOFF, WORDMASK, 2, true> : k_stream_ws<ROTOFF, WORDMASK, 2, false>;
+}
+static stream_kernel_t pick_kernel_ws(const KParams &kp, bool raw)
+{
+    if (kp.mw >= 20) return pick2_ws<17, 0x1FFFCu>(kp.prew, raw);
+    if (kp.mw == 16) return pick2_ws<13, 0x1FFCu>(kp.prew, raw);
+    if (kp.mw == 12) return pick2_ws<9, 0x1FCu>(kp.prew, raw);
+    return nullptr;
+}
+static size_t stream_smem_bytes_ws(u32 bitmap_bytes)
+{
+    return ((bitmap_bytes + 127u) & ~127u) + (size_t)WS_NS * WS_TBUF + sizeof(WsSmem) + 64;
+}
+
+template <int ROTOFF, u32 WORDMASK>
 static stream_kernel_t pick2(int prew, bool raw)
 {
     if (prew == 1) return raw ? k_stream<ROTOFF, WORDMASK, 1, true> : k_stream<ROTOFF, WORDMASK, 1, false>;
@@ -819,18 +1193,22 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         return MK_ERR_ARG;
     }
     const KParams &kp = ctx->kp;
-    stream_kernel_t kern = pick_kernel(kp, raw_mode);
+    // MK_STREAM_IMPL=classic selects the unit-pulling kernel (k_stream); default: warp-specialised
+    const char *impl = getenv("MK_STREAM_IMPL");
+    const bool ws = !(impl && !strcmp(impl, "classic"));
+    stream_kernel_t kern = ws ? pick_kernel_ws(kp, raw_mode) : pick_kernel(kp, raw_mode);
     if (!kern) {
         snprintf(ctx->err, sizeof(ctx->err), "unsupported inner substring width subk=%d", kp.subk);
         return MK_ERR_UNSUPPORTED;
     }
     // tile-proper bytes: a multiple of 64 (two 32-byte probe blocks per scanning thread)
-    u32 tile_bytes = raw_mode ? 16384u : (u32)MK_MAX_TILE;
+    const u32 max_tile = ws ? (u32)WS_TILE : (u32)MK_MAX_TILE;
+    u32 tile_bytes = raw_mode ? 16384u : max_tile;
     if (const char *e = getenv(raw_mode ? "MK_RAW_TILE_BYTES" : "MK_TILE_BYTES")) {
         u32 v = (u32)atoi(e);
         v &= ~63u;
         if (v < 64u) v = 64u;
-        if (v > MK_MAX_TILE) v = MK_MAX_TILE;
+        if (v > max_tile) v = max_tile;
         tile_bytes = v;
     }
     u64 n_tiles64 = (nbytes + tile_bytes - 1) / tile_bytes;
@@ -844,7 +1222,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     double rate = 2.0 * (double)kp.dim_end / (double)(1ull << (4 * kp.subk)) + 0.001;
     if (rate > 1.0) rate = 1.0;
     u64 cap = (u64)((double)nbytes * rate * 0.75) + 65536;
-    size_t smem = stream_smem_bytes(ctx->bitmap_words * 4);
+    size_t smem = ws ? stream_smem_bytes_ws(ctx->bitmap_words * 4) : stream_smem_bytes(ctx->bitmap_words * 4);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int attempt = 0; attempt < 2; attempt++) {
@@ -862,7 +1240,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp; a.trace = (u64 *)ctx->d_trace; a.wd = counters + 8;
         u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        kern<<<grid, MK_STREAM_THREADS, smem, ctx->stream>>>(a);
+        kern<<<grid, ws ? WS_THREADS : MK_STREAM_THREADS, smem, ctx->stream>>>(a);
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         LAUNCH_COUNT(ctx);
         CK(cudaGetLastError());

@@ -709,15 +709,28 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 // The k-th tile of a CTA always uses stage k % WS_NS, so every role derives stage and mbarrier
 // parity from its own loop counter.
 // ================================================================================================
-#define WS_NS 4
-#define WS_TILE 16384
+#ifndef WS_NS
+#define WS_NS 5        // ring stages
+#endif
+#ifndef WS_TILE
+#define WS_TILE 12288  // tile-proper bytes (multiple of 2048)
+#endif
 #define WS_BLK (WS_TILE / 32)
 #define WS_CHUNK (WS_TILE / 2048)
-#define WS_NSW 4   // scan warps
-#define WS_NMW 2   // mask warps
+#ifndef WS_NSW
+#define WS_NSW 6       // scan warps
+#endif
+#ifndef WS_NMW
+#define WS_NMW 6       // mask warps
+#endif
 #define WS_NFW (WS_NSW + WS_NMW)
-#define WS_NPW 10  // probe warps
-#define WS_THREADS (32 * (2 + WS_NFW + WS_NPW))
+#ifndef WS_NPG
+#define WS_NPG 2       // probe groups: group g probes the tiles with k % WS_NPG == g
+#endif
+#ifndef WS_NPW
+#define WS_NPW 7       // probe warps per group
+#endif
+#define WS_THREADS (32 * (2 + WS_NFW + WS_NPG * WS_NPW))
 #define WS_TBUF (MK_HALO + WS_TILE + 96)
 
 struct WsStage {
@@ -795,14 +808,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
     if (wid == 0) {
         // ======================= loader =========================================================
         if (lane == 0) {
+            u32 ended = 0;
             for (u32 k = 0;; k++) {
                 const u32 s = k % WS_NS, v = k / WS_NS;
                 if (v > 0 && !wait_on(&S.done[s], (v - 1) & 1u, 10, k)) break;
                 stamp(k, 0);
                 S.n_items[s] = 0;
-                const u32 t = atomicAdd(A.tile_counter, 1u);
+                const u32 t = ended ? 0xFFFFFFFFu : atomicAdd(A.tile_counter, 1u);
                 S.tile[s] = t;
-                if (t >= A.n_tiles) { mbar_arrive(&S.full[s]); break; }   // end marker for every role
+                if (t >= A.n_tiles) {       // end marker: one per probe group, in consecutive ring slots
+                    mbar_arrive(&S.full[s]);
+                    if (++ended == WS_NPG) break;
+                    continue;
+                }
                 const u32 tb = tile_len(t);
                 uint8_t *dst = tbuf + s * WS_TBUF;
                 const uint8_t *src = A.text + (u64)t * TB;
@@ -832,15 +850,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 // newlines before t = newlines through prev_t + counts of the tiles in between
                 u64 sum = 0;
                 bool ok = true;
-                for (long long i0 = prev_t + 1; i0 < (long long)t; i0 += 128) {
-                    u64 d[4];
+                for (long long i0 = prev_t + 1; i0 < (long long)t; i0 += 256) {
+                    u64 d[8];
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++) {
+                    for (int k4 = 0; k4 < 8; k4++) {
                         long long idx = i0 + 32 * k4 + (long long)lane;
                         d[k4] = idx < (long long)t ? ld_volatile_u64(&A.tile_desc[idx]) : (1ull << 62);
                     }
 #pragma unroll
-                    for (int k4 = 0; k4 < 4; k4++) {
+                    for (int k4 = 0; k4 < 8; k4++) {
                         long long idx = i0 + 32 * k4 + (long long)lane;
                         for (u32 n = 0; (d[k4] >> 62) == 0; n++) {
                             if (n > WD_LIMIT) { watchdog(22, t, (u64)idx, (u64)prev_t, k); ok = false; break; }
@@ -923,12 +941,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 u32 v = lane < NCHUNK ? G.ctot[lane] : 0;
                 u32 incl = v;
 #pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
+                for (int o = 1; o < 16; o <<= 1) {
                     u32 x = __shfl_up_sync(0xffffffffu, incl, o);
                     if (lane >= (u32)o) incl += x;
                 }
                 if (lane < NCHUNK) G.cpre[lane] = incl - v;
-                const u32 total = __shfl_sync(0xffffffffu, incl, 7);    // WS_CHUNK == 8 lanes carry values
+                const u32 total = __shfl_sync(0xffffffffu, incl, 15);   // WS_CHUNK <= 16 lanes carry values
                 if (lane == 0) {
                     S.tot[s] = total;
                     st_volatile_u64(&A.tile_desc[t], (1ull << 62) | (u64)total);
@@ -993,14 +1011,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 stamp(k, 1);
             }
         } else {
+            u32 ended = 0;
             for (u32 k = 0;; k++) {
                 const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
                 if (!wait_on(&S.full[s], par, 32, k)) break;
                 const u32 t = S.tile[s];
-                if (t >= A.n_tiles) {                       // end marker: wake the probe warps and leave
+                if (t >= A.n_tiles) {                       // end markers: wake every probe group, then leave
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.ready[s]);
-                    break;
+                    if (++ended == WS_NPG) break;
+                    continue;
                 }
                 if (!wait_on(&S.resolved[s], par, 31, k)) break;
                 stamp(k, 2);
@@ -1010,8 +1030,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         }
     } else {
         // ======================= probe ==========================================================
-        const u32 pw = wid - 2 - WS_NFW;
-        for (u32 k = 0;; k++) {
+        const u32 pg = (wid - 2 - WS_NFW) / WS_NPW, pw = (wid - 2 - WS_NFW) % WS_NPW;
+        for (u32 k = pg;; k += WS_NPG) {
             const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
             stamp(k, 0);
             if (!wait_on(&S.ready[s], par, 40, k)) break;
@@ -1022,7 +1042,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             const uint8_t *tx = tbuf + s * WS_TBUF;
             const u64 T = (u64)t * TB;
             const u32 n = S.n_items[s];
-            for (u32 r = (pw + WS_NPW - (k % WS_NPW)) % WS_NPW; r * 32u < n; r += WS_NPW) {
+            for (u32 r = (pw + WS_NPW - ((k / WS_NPG) % WS_NPW)) % WS_NPW; r * 32u < n; r += WS_NPW) {
                 const u32 it = r * 32u + lane;
                 if (it < n) {
                     const u32 b = G.items[it];
@@ -1203,7 +1223,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     }
     // tile-proper bytes: a multiple of 64 (two 32-byte probe blocks per scanning thread)
     const u32 max_tile = ws ? (u32)WS_TILE : (u32)MK_MAX_TILE;
-    u32 tile_bytes = raw_mode ? 16384u : max_tile;
+    u32 tile_bytes = raw_mode ? (max_tile < 16384u ? max_tile : 16384u) : max_tile;
     if (const char *e = getenv(raw_mode ? "MK_RAW_TILE_BYTES" : "MK_TILE_BYTES")) {
         u32 v = (u32)atoi(e);
         v &= ~63u;

@@ -710,7 +710,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 // parity from its own loop counter.
 // ================================================================================================
 #ifndef WS_NS
-#define WS_NS 5        // ring stages
+#define WS_NS 6        // ring stages
 #endif
 #ifndef WS_TILE
 #define WS_TILE 12288  // tile-proper bytes (multiple of 2048)
@@ -730,12 +730,19 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 #ifndef WS_NPW
 #define WS_NPW 7       // probe warps per group
 #endif
-#define WS_THREADS (32 * (2 + WS_NFW + WS_NPG * WS_NPW))
+#ifndef WS_NRES
+#define WS_NRES 1       // resolver warps (tile k is resolved by warp 1 + k % WS_NRES)
+#endif
+#define WS_ROLE0 (1 + WS_NRES)   // first front-end warp
+#define WS_THREADS (32 * (WS_ROLE0 + WS_NFW + WS_NPG * WS_NPW))
+#ifndef WS_PF_DIST
+#define WS_PF_DIST 3    // L2 prefetch distance in units of gridDim tiles
+#endif
 #define WS_TBUF (MK_HALO + WS_TILE + 96)
 
 struct WsStage {
-    u32 nlm[WS_BLK];
-    u32 posmask[WS_BLK];
+    u32 nlm[WS_BLK];             // newline mask of each block; the mask warps overwrite it in place with
+                                 // the block's sequence-byte mask (same index, same thread)
     uint16_t exw[WS_BLK];
     uint16_t items[WS_BLK];
     u32 ctot[WS_CHUNK];
@@ -744,10 +751,15 @@ struct WsStage {
 struct WsSmem {
     WsStage st[WS_NS];
     u64 full[WS_NS], scanned[WS_NS], resolved[WS_NS], ready[WS_NS], done[WS_NS];
-    u64 P[WS_NS];
+    u64 P[WS_NS];                // newlines before the tile (its first byte's line number)
+    u64 incl[WS_NS];             // newlines through the tile (handed from one resolver warp to the next)
     u32 tile[WS_NS], n_items[WS_NS], scnt[WS_NS], tot[WS_NS];
 };
 
+__device__ __forceinline__ void prefetch_l2(const void *p, u32 bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(u64 *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -830,26 +842,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 fence_proxy_async();
                 mbar_expect_tx(&S.full[s], bytes);
                 tma_load_1d(dst, src, bytes, &S.full[s]);
+                // Tickets are handed out in file order, so the tile WS_PF_DIST x gridDim ahead will be
+                // claimed by some CTA a few tile periods from now: pull it into L2 already.
+                const u64 pf = (u64)t + (u64)WS_PF_DIST * gridDim.x;
+                if (pf < A.n_tiles) {
+                    const u64 o = pf * TB;
+                    const u64 rem = A.nbytes - o;
+                    prefetch_l2(A.text + o, (u32)((rem < TB ? rem : TB) + 15u) & ~15u);
+                }
             }
         }
-    } else if (wid == 1) {
-        // ======================= resolver =======================================================
-        long long prev_t = -1;
-        u64 prev_incl = 0;
+    } else if (wid <= WS_NRES) {
+        // ======================= resolvers ======================================================
+        // newlines before tile t_k = newlines through t_{k-1} (this CTA's previous tile) + the counts
+        // other CTAs published for the tickets in between.  Those counts appear when the other CTAs
+        // finish scanning, i.e. at about the time our own scan finishes, and reading them costs an
+        // L2 round trip: WS_NRES warps take turns so that this latency overlaps across tiles.
+        const u32 rw = wid - 1;
         const u64 VMASK = (1ull << 62) - 1;
-        for (u32 k = 0;; k++) {
+        for (u32 k = rw;; k += WS_NRES) {
             const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
             if (!wait_on(&S.full[s], par, 20, k)) break;
             const u32 t = S.tile[s];
             if (t >= A.n_tiles) break;
+            const u32 sp = (k + WS_NS - 1) % WS_NS, parp = ((k - 1) / WS_NS) & 1u;   // previous tile's stage
+            const long long prev_t = k ? (long long)S.tile[sp] : -1;
             stamp(k, 0);
-            if (!wait_on(&S.scanned[s], par, 21, k)) break;
-            stamp(k, 1);
+            u64 sum = 0;
+            bool ok = true;
             if (!RAW) {
-                const u32 total = S.tot[s];
-                // newlines before t = newlines through prev_t + counts of the tiles in between
-                u64 sum = 0;
-                bool ok = true;
                 for (long long i0 = prev_t + 1; i0 < (long long)t; i0 += 256) {
                     u64 d[8];
 #pragma unroll
@@ -868,22 +889,30 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                         sum += d[k4] & VMASK;
                     }
                 }
-                const u64 excl = prev_incl + warp_sum_u64(sum);
-                prev_t = (long long)t;
-                prev_incl = excl + total;
-                if (lane == 0) {
-                    S.P[s] = A.line_base + excl;
-                    if (t == A.n_tiles - 1) *A.total_newlines = A.line_base + excl + total;
-                }
+                sum = warp_sum_u64(sum);
                 if (!__all_sync(0xffffffffu, ok)) break;
+            }
+            if (!wait_on(&S.scanned[s], par, 21, k)) break;   // our own count (S.tot) is final
+            stamp(k, 1);
+            u64 prev_incl = 0;
+            if (k) {                                     // chained through shared memory
+                if (!wait_on(&S.resolved[sp], parp, 23, k)) break;
+                prev_incl = S.incl[sp];
+            }
+            if (lane == 0) {
+                const u64 excl = prev_incl + sum;
+                const u32 total = RAW ? 0u : S.tot[s];
+                S.P[s] = A.line_base + excl;
+                S.incl[s] = excl + total;
+                if (!RAW && t == A.n_tiles - 1) *A.total_newlines = A.line_base + excl + total;
             }
             stamp(k, 2);
             __syncwarp();
             if (lane == 0) { __threadfence_block(); mbar_arrive(&S.resolved[s]); }
         }
-    } else if (wid < 2 + WS_NFW) {
+    } else if (wid < WS_ROLE0 + WS_NFW) {
         // ======================= front end: scan warps and mask warps ==============================
-        const u32 fw = wid - 2;
+        const u32 fw = wid - WS_ROLE0;
         auto scan = [&](u32 s, u32 t) {
             WsStage &G = S.st[s];
             uint8_t *tx = tbuf + s * WS_TBUF;
@@ -982,7 +1011,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                             }
                             pm[h] = (p0 ^ ((tgt & 1u) ? 0u : ~0u)) & (p1 ^ ((tgt & 2u) ? 0u : ~0u)) & ~nl;
                         }
-                        G.posmask[b] = pm[h];
+                        G.nlm[b] = pm[h];
                     }
                 }
                 const u32 ma = __ballot_sync(0xffffffffu, pm[0] != 0);
@@ -1030,7 +1059,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         }
     } else {
         // ======================= probe ==========================================================
-        const u32 pg = (wid - 2 - WS_NFW) / WS_NPW, pw = (wid - 2 - WS_NFW) % WS_NPW;
+        const u32 pg = (wid - WS_ROLE0 - WS_NFW) / WS_NPW, pw = (wid - WS_ROLE0 - WS_NFW) % WS_NPW;
         for (u32 k = pg;; k += WS_NPG) {
             const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
             stamp(k, 0);
@@ -1048,7 +1077,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     const u32 b = G.items[it];
                     u32 Aw[4];
                     u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
-                    hits &= G.posmask[b];
+                    hits &= G.nlm[b];                       // sequence-byte mask by now
                     while (hits) {
                         u32 j = __ffs(hits) - 1;
                         hits &= hits - 1;

@@ -28,6 +28,7 @@ struct StreamArgs {
     u32 n_tiles;
     u64 *tile_desc;
     u32 *tile_counter;
+    u32 *count_counter;     // tickets of the count-ahead pass (k_stream_ws)
     const u32 *bitmap;
     u32 bitmap_bytes;
     const u64 *ptab;
@@ -58,23 +59,32 @@ __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+#ifndef MK_WAIT_HINT
+#define MK_WAIT_HINT 0x989680   // try_wait suspend-time hint (ns): waiting warps sleep in hardware instead of polling
+#endif
 __device__ __forceinline__ u32 mbar_try_wait(u64 *bar, u32 parity)
 {
     u32 ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"((u32)MK_WAIT_HINT)
         : "memory");
     return ok;
 }
+// false = gave up (the caller raises the watchdog flag); every failed try_wait suspends the warp for
+// a short hardware-defined time, so the loop is kept to the bare minimum of instructions
 __device__ __forceinline__ bool mbar_wait(u64 *bar, u32 parity)
 {
     for (u32 n = 0; !mbar_try_wait(bar, parity); n++)
         if (n > WD_LIMIT) return false;
     return true;
+}
+__device__ __forceinline__ void named_bar_sync(u32 id, u32 nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async()
 {
@@ -149,8 +159,10 @@ __device__ __forceinline__ u64 tile_lookback(u64 *desc, u32 tile, u64 agg)
     for (;;) {
         long long idx = look - (long long)lane;
         u64 d;
+        u32 spins = 0;
         do {
             d = idx >= 0 ? ld_volatile_u64(&desc[idx]) : (2ull << 62);
+            if (++spins > WD_LIMIT) return ~0ull;      // gave up (the caller raises the watchdog flag)
         } while (__any_sync(0xffffffffu, (d >> 62) == 0));
         u32 m2 = __ballot_sync(0xffffffffu, (d >> 62) == 2);
         u64 val = d & VMASK;
@@ -730,10 +742,16 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 #ifndef WS_NPW
 #define WS_NPW 7       // probe warps per group
 #endif
-#ifndef WS_NRES
-#define WS_NRES 1       // resolver warps (tile k is resolved by warp 1 + k % WS_NRES)
+#ifndef WS_NCW
+#define WS_NCW 4        // count-ahead warps
 #endif
-#define WS_ROLE0 (1 + WS_NRES)   // first front-end warp
+#ifndef WS_WINDOW
+#define WS_WINDOW 3     // the count pass may run this many x gridDim tiles ahead of the load front
+#endif
+#ifndef WS_G
+#define WS_G 4          // tiles per ticket (consecutive tiles of one CTA)
+#endif
+#define WS_ROLE0 (2 + WS_NCW)   // first front-end warp (0 = loader, 1 = resolver, then the count warps)
 #define WS_THREADS (32 * (WS_ROLE0 + WS_NFW + WS_NPG * WS_NPW))
 #ifndef WS_PF_DIST
 #define WS_PF_DIST 3    // L2 prefetch distance in units of gridDim tiles
@@ -750,15 +768,39 @@ struct WsStage {
 };
 struct WsSmem {
     WsStage st[WS_NS];
-    u64 full[WS_NS], scanned[WS_NS], resolved[WS_NS], ready[WS_NS], done[WS_NS];
-    u64 P[WS_NS];                // newlines before the tile (its first byte's line number)
-    u64 incl[WS_NS];             // newlines through the tile (handed from one resolver warp to the next)
+    u64 full[WS_NS], scanned[WS_NS], ready[WS_NS], done[WS_NS];
+    u64 gready[2], gfree[2];     // group mailbox resolver -> loader
+    u64 gq_P[2];
+    u32 gq_g[2];
+    u32 cticket, csum;           // count team: current group ticket, its newline count so far
+    u32 abort;                   // a leader's wait gave up: the whole role leaves
+    u64 Pn[2 * WS_NS];           // newlines before the k-th tile of this CTA (index k % (2 NS))
     u32 tile[WS_NS], n_items[WS_NS], scnt[WS_NS], tot[WS_NS];
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p, u32 bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+#ifndef WS_CNT_BATCH
+#define WS_CNT_BATCH 12 // 16-byte loads in flight per lane of a count warp
+#endif
+__device__ __forceinline__ uint4 ld_nc_u128(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p)
+{
+    u32 v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ld_volatile_v2(const u64 *p, u32 &lo, u32 &hi)
+{
+    asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(u64 *bar)
 {
@@ -785,11 +827,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         for (int s = 0; s < WS_NS; s++) {
             mbar_init(&S.full[s], 1);
             mbar_init(&S.scanned[s], WS_NSW);
-            mbar_init(&S.resolved[s], 1);
             mbar_init(&S.ready[s], WS_NMW);
             mbar_init(&S.done[s], WS_NPW);
-            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.P[s] = 0; S.scnt[s] = 0; S.tot[s] = 0;
+            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0; S.tot[s] = 0;
         }
+        for (int q = 0; q < 2; q++) { mbar_init(&S.gready[q], 1); mbar_init(&S.gfree[q], 1); }
+        S.cticket = 0; S.csum = 0; S.abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();   // the only block-wide barrier of the kernel
@@ -798,6 +841,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
     const u32 NBLK = TB / 32;
     const u32 NCHUNK = (TB + 2047u) / 2048u;
     const u32 NMUNIT = (NBLK + 63u) / 64u;
+    const u32 n_groups = (A.n_tiles + WS_G - 1) / WS_G;
     auto tile_len = [&](u32 t) -> u32 {
         u64 rem = A.nbytes - (u64)t * TB;
         return rem < TB ? (u32)rem : TB;
@@ -817,22 +861,56 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         return false;
     };
 
+    // A multi-warp role waits through its leader warp: only the leader polls the mbarrier, the other
+    // warps block on a named barrier, which costs no issue slots while they wait.
+    auto role_wait = [&](u64 *bar, u64 *bar2, u32 parity, u32 site, u32 k, u32 barid, u32 nwarps, bool leader) -> bool {
+        if (leader) {
+            bool ok = mbar_wait(bar, parity);
+            if (ok && bar2) ok = mbar_wait(bar2, parity);
+            if (!ok && lane == 0) { watchdog(site, k, parity, wid, 0); S.abort = 1; }
+        }
+        named_bar_sync(barid, 32u * nwarps);
+        return *(volatile u32 *)&S.abort == 0;
+    };
+
     if (wid == 0) {
         // ======================= loader =========================================================
+        // One lane.  Tickets are groups of WS_G consecutive tiles; the resolver warp hands over the next
+        // group and the line number of its first tile through a two-slot mailbox, so a freed stage is
+        // refilled without any global round trip.
         if (lane == 0) {
-            u32 ended = 0;
+            u32 ended = 0, j = 0, g = 0, i = 0, cnt = 0;
+            u64 P = 0;
+            bool finished = false;
             for (u32 k = 0;; k++) {
                 const u32 s = k % WS_NS, v = k / WS_NS;
                 if (v > 0 && !wait_on(&S.done[s], (v - 1) & 1u, 10, k)) break;
                 stamp(k, 0);
+                if (!finished && i == cnt) {            // next group of this CTA
+                    const u32 slot = j & 1u;
+                    if (!wait_on(&S.gready[slot], (j >> 1) & 1u, 11, k)) break;
+                    g = S.gq_g[slot];
+                    P = S.gq_P[slot];
+                    mbar_arrive(&S.gfree[slot]);
+                    j++;
+                    if (g >= n_groups) finished = true;
+                    else {
+                        i = 0;
+                        const u32 left = A.n_tiles - g * WS_G;
+                        cnt = left < (u32)WS_G ? left : (u32)WS_G;
+                    }
+                }
+                const u32 t = finished ? 0xFFFFFFFFu : g * WS_G + i;
                 S.n_items[s] = 0;
-                const u32 t = ended ? 0xFFFFFFFFu : atomicAdd(A.tile_counter, 1u);
                 S.tile[s] = t;
                 if (t >= A.n_tiles) {       // end marker: one per probe group, in consecutive ring slots
                     mbar_arrive(&S.full[s]);
                     if (++ended == WS_NPG) break;
                     continue;
                 }
+                if (i == 0) S.Pn[k % (2 * WS_NS)] = A.line_base + P;   // (later tiles of the group: scan finisher)
+                i++;
+                stamp(k, 1);
                 const u32 tb = tile_len(t);
                 uint8_t *dst = tbuf + s * WS_TBUF;
                 const uint8_t *src = A.text + (u64)t * TB;
@@ -842,78 +920,164 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 fence_proxy_async();
                 mbar_expect_tx(&S.full[s], bytes);
                 tma_load_1d(dst, src, bytes, &S.full[s]);
-                // Tickets are handed out in file order, so the tile WS_PF_DIST x gridDim ahead will be
-                // claimed by some CTA a few tile periods from now: pull it into L2 already.
-                const u64 pf = (u64)t + (u64)WS_PF_DIST * gridDim.x;
-                if (pf < A.n_tiles) {
-                    const u64 o = pf * TB;
-                    const u64 rem = A.nbytes - o;
-                    prefetch_l2(A.text + o, (u32)((rem < TB ? rem : TB) + 15u) & ~15u);
+                if (RAW) {                  // (FASTQ mode: the count-ahead pass has pulled the tile into L2)
+                    const u64 pf = (u64)t + (u64)WS_PF_DIST * gridDim.x * WS_G;
+                    if (pf < A.n_tiles) {
+                        const u64 o = pf * TB;
+                        const u64 rem = A.nbytes - o;
+                        prefetch_l2(A.text + o, (u32)((rem < TB ? rem : TB) + 15u) & ~15u);
+                    }
                 }
             }
         }
-    } else if (wid <= WS_NRES) {
-        // ======================= resolvers ======================================================
-        // newlines before tile t_k = newlines through t_{k-1} (this CTA's previous tile) + the counts
-        // other CTAs published for the tickets in between.  Those counts appear when the other CTAs
-        // finish scanning, i.e. at about the time our own scan finishes, and reading them costs an
-        // L2 round trip: WS_NRES warps take turns so that this latency overlaps across tiles.
-        const u32 rw = wid - 1;
-        const u64 VMASK = (1ull << 62) - 1;
-        for (u32 k = rw;; k += WS_NRES) {
-            const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
-            if (!wait_on(&S.full[s], par, 20, k)) break;
-            const u32 t = S.tile[s];
-            if (t >= A.n_tiles) break;
-            const u32 sp = (k + WS_NS - 1) % WS_NS, parp = ((k - 1) / WS_NS) & 1u;   // previous tile's stage
-            const long long prev_t = k ? (long long)S.tile[sp] : -1;
-            stamp(k, 0);
-            u64 sum = 0;
-            bool ok = true;
-            if (!RAW) {
-                for (long long i0 = prev_t + 1; i0 < (long long)t; i0 += 256) {
-                    u64 d[8];
+    } else if (wid == 1) {
+        // ======================= resolver =======================================================
+        // Claims this CTA's groups one to two ahead of the loader and computes the number of newlines
+        // before each: newlines through the CTA's previous group + the group counts the count-ahead
+        // pass published for the tickets in between (one look-back per WS_G tiles, off the ring).
+        u64 run_incl = 0;
+        long long prev_g = -1;
+        for (u32 j = 0;; j++) {
+            const u32 slot = j & 1u;
+            if (j >= 2 && !wait_on(&S.gfree[slot], ((j >> 1) - 1u) & 1u, 20, j)) break;
+            u32 g = 0;
+            if (lane == 0) g = atomicAdd(A.tile_counter, 1u);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            u64 P = 0;
+            if (!RAW && g < n_groups) {
+                u32 sum = 0, own = 0;
+                bool good = true;
+                for (long long i0 = prev_g + 1; i0 <= (long long)g; i0 += 256) {
+                    u32 lo[8], hi[8];
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; k4++) {
-                        long long idx = i0 + 32 * k4 + (long long)lane;
-                        d[k4] = idx < (long long)t ? ld_volatile_u64(&A.tile_desc[idx]) : (1ull << 62);
+                    for (int q = 0; q < 8; q++) {
+                        const long long idx = i0 + 32 * q + (long long)lane;
+                        lo[q] = 0; hi[q] = 1u << 30;
+                        if (idx <= (long long)g) ld_volatile_v2(&A.tile_desc[idx], lo[q], hi[q]);
                     }
 #pragma unroll
-                    for (int k4 = 0; k4 < 8; k4++) {
-                        long long idx = i0 + 32 * k4 + (long long)lane;
-                        for (u32 n = 0; (d[k4] >> 62) == 0; n++) {
-                            if (n > WD_LIMIT) { watchdog(22, t, (u64)idx, (u64)prev_t, k); ok = false; break; }
-                            __nanosleep(100);
-                            d[k4] = ld_volatile_u64(&A.tile_desc[idx]);
+                    for (int q = 0; q < 8; q++) {
+                        const long long idx = i0 + 32 * q + (long long)lane;
+                        for (u32 n = 0; (hi[q] >> 30) == 0; n++) {
+                            if (n > WD_LIMIT) { watchdog(22, g, (u64)idx, (u64)prev_g, j); good = false; break; }
+                            __nanosleep(200);
+                            ld_volatile_v2(&A.tile_desc[idx], lo[q], hi[q]);
                         }
-                        sum += d[k4] & VMASK;
+                        if (idx == (long long)g) own = lo[q]; else sum += lo[q];
                     }
                 }
-                sum = warp_sum_u64(sum);
-                if (!__all_sync(0xffffffffu, ok)) break;
-            }
-            if (!wait_on(&S.scanned[s], par, 21, k)) break;   // our own count (S.tot) is final
-            stamp(k, 1);
-            u64 prev_incl = 0;
-            if (k) {                                     // chained through shared memory
-                if (!wait_on(&S.resolved[sp], parp, 23, k)) break;
-                prev_incl = S.incl[sp];
+                sum = __reduce_add_sync(0xffffffffu, sum);
+                own = __reduce_add_sync(0xffffffffu, own);
+                if (!__all_sync(0xffffffffu, good)) break;
+                P = run_incl + sum;
+                run_incl = P + own;
+                prev_g = (long long)g;
+                if (lane == 0 && g == n_groups - 1) *A.total_newlines = A.line_base + run_incl;
             }
             if (lane == 0) {
-                const u64 excl = prev_incl + sum;
-                const u32 total = RAW ? 0u : S.tot[s];
-                S.P[s] = A.line_base + excl;
-                S.incl[s] = excl + total;
-                if (!RAW && t == A.n_tiles - 1) *A.total_newlines = A.line_base + excl + total;
+                S.gq_g[slot] = g;
+                S.gq_P[slot] = P;
+                __threadfence_block();
+                mbar_arrive(&S.gready[slot]);
             }
-            stamp(k, 2);
-            __syncwarp();
-            if (lane == 0) { __threadfence_block(); mbar_arrive(&S.resolved[s]); }
+            if (g >= n_groups) break;
+        }
+    } else if (wid < WS_ROLE0) {
+        // ======================= count-ahead pass ===============================================
+        // Record structure needs the number of '\n' before every tile.  Counting is cheap and has no
+        // dependencies, so it runs ahead of the pipeline on its own tickets, straight from global
+        // memory (which also pulls the tile into L2 for the TMA load that follows), and publishes one
+        // descriptor per tile.
+        if (!RAW) {
+            const u32 window = (u32)WS_WINDOW * gridDim.x;
+            // The WS_NCW count warps of the CTA work as a team on one group ticket (its tiles interleaved
+            // among them), so a group's count is complete one tile-time after it was claimed.
+            const u32 cw = wid - 2;
+            for (;;) {
+                if (cw == 0 && lane == 0) {
+                    u32 c = atomicAdd(A.count_counter, 1u);
+                    if (c >= window && c < n_groups) {   // flow control against the load front
+                        for (u32 n = 0; c >= ld_volatile_u32(A.tile_counter) + window; n++) {
+                            if (n > WD_LIMIT) { watchdog(50, c, 0, 0, 0); c = 0xFFFFFFFFu; break; }
+                            __nanosleep(256);
+                        }
+                    }
+                    S.cticket = c;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * WS_NCW) : "memory");
+                const u32 c = S.cticket;
+                if (c >= n_groups) break;
+                u32 gtotal = 0;
+                for (u32 i = cw; i < (u32)WS_G; i += WS_NCW) {
+                    const u32 t = c * WS_G + i;
+                    if (t >= A.n_tiles) break;
+                    const u32 tb = tile_len(t);
+                    const uint8_t *base = A.text + (u64)t * TB;
+                    {   // the tile this warp is likely to count a group from now: into L2 already
+                        const u64 pf = (u64)t + (u64)gridDim.x * WS_G;
+                        if (lane == 0 && pf < A.n_tiles) {
+                            const u64 o = pf * TB, rem = A.nbytes - o;
+                            prefetch_l2(A.text + o, (u32)((rem < TB ? rem : TB) + 15u) & ~15u);
+                        }
+                    }
+                    u32 acc_lo = 0, acc_hi = 0;         // per-byte-lane counters, folded to 16 bit per batch
+                    if (tb == TB && TB % (512u * WS_CNT_BATCH) == 0) {
+                        // full tile: WS_CNT_BATCH independent 16-byte loads per lane in flight, 4 instructions
+                        // per word (the last one, f >> 7 accumulated, on the FMA pipe)
+                        for (u32 v0 = 0; v0 < TB / 16u; v0 += 32u * WS_CNT_BATCH) {
+                            uint4 q[WS_CNT_BATCH];
+#pragma unroll
+                            for (int jj = 0; jj < WS_CNT_BATCH; jj++) q[jj] = ld_nc_u128(base + 16u * (v0 + 32u * jj + lane));
+                            u32 acc = 0;
+#pragma unroll
+                            for (int jj = 0; jj < WS_CNT_BATCH; jj++) {
+                                u32 w[4] = {q[jj].x, q[jj].y, q[jj].z, q[jj].w};
+#pragma unroll
+                                for (int x = 0; x < 4; x++) {
+                                    u32 t7 = ((w[x] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                                    u32 f = ~(t7 | w[x]) & 0x80808080u;     // 0x80 where the byte is a newline
+                                    acc = __umulhi(f, 1u << 25) + acc;      // += f >> 7 (<= 4 * WS_CNT_BATCH per byte lane)
+                                }
+                            }
+                            acc_lo += acc & 0x00FF00FFu;
+                            acc_hi += (acc >> 8) & 0x00FF00FFu;
+                        }
+                    } else {
+                        const u32 nvec = (tb + 15u) >> 4;
+                        for (u32 v = lane; v < nvec; v += 32u) {
+                            uint4 q = ld_nc_u128(base + 16u * v);
+                            u32 w[4] = {q.x, q.y, q.z, q.w};
+                            u32 acc = 0;
+#pragma unroll
+                            for (int x = 0; x < 4; x++) {
+                                u32 t7 = ((w[x] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                                u32 f = ~(t7 | w[x]) & 0x80808080u;
+                                const u32 o = 16u * v + 4u * x;
+                                if (o + 4u > tb) f &= o >= tb ? 0u : ((1u << (8u * (tb - o))) - 1u);   // end of the text
+                                acc += f >> 7;
+                            }
+                            acc_lo += acc & 0x00FF00FFu;
+                            acc_hi += (acc >> 8) & 0x00FF00FFu;
+                        }
+                    }
+                    u32 total = acc_lo + acc_hi;
+                    total = (total & 0xFFFFu) + (total >> 16);
+                    total = __reduce_add_sync(0xffffffffu, total);
+                    if (lane == 0 && total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
+                    gtotal += total;
+                }
+                if (lane == 0 && gtotal) atomicAdd(&S.csum, gtotal);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * WS_NCW) : "memory");
+                if (cw == 0 && lane == 0) {
+                    st_volatile_u64(&A.tile_desc[c], (1ull << 62) | (u64)S.csum);
+                    S.csum = 0;     // (the team adds to it again only after the next barrier)
+                }
+            }
         }
     } else if (wid < WS_ROLE0 + WS_NFW) {
         // ======================= front end: scan warps and mask warps ==============================
         const u32 fw = wid - WS_ROLE0;
-        auto scan = [&](u32 s, u32 t) {
+        auto scan = [&](u32 s, u32 t, u32 k) {
             WsStage &G = S.st[s];
             uint8_t *tx = tbuf + s * WS_TBUF;
             const u32 tb = tile_len(t);
@@ -975,21 +1139,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     if (lane >= (u32)o) incl += x;
                 }
                 if (lane < NCHUNK) G.cpre[lane] = incl - v;
-                const u32 total = __shfl_sync(0xffffffffu, incl, 15);   // WS_CHUNK <= 16 lanes carry values
-                if (lane == 0) {
-                    S.tot[s] = total;
-                    st_volatile_u64(&A.tile_desc[t], (1ull << 62) | (u64)total);
-                    if (total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
-                }
+                // later tiles of a group take their line number from the tile before them
+                if (lane == 15 && (t + 1) % WS_G != 0) S.Pn[(k + 1) % (2 * WS_NS)] = S.Pn[k % (2 * WS_NS)] + incl;
             }
             if (old == WS_NSW - 1 && lane == 0) S.scnt[s] = 0;
             __syncwarp();
             if (lane == 0) { __threadfence_block(); mbar_arrive(&S.scanned[s]); }
         };
-        auto mask = [&](u32 s, u32 t) {
+        auto mask = [&](u32 s, u32 t, u32 k) {
             WsStage &G = S.st[s];
             const u32 tb = tile_len(t);
-            const u32 P = RAW ? 0u : (u32)S.P[s];
+            const u32 P = RAW ? 0u : (u32)S.Pn[k % (2 * WS_NS)];
             for (u32 u = fw - WS_NSW; u < NMUNIT; u += WS_NMW) {
                 u32 pm[2];
 #pragma unroll
@@ -1032,18 +1192,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             // soon as their text has landed, which is what keeps every CTA's resolver fast
             for (u32 k = 0;; k++) {
                 const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
-                if (!wait_on(&S.full[s], par, 30, k)) break;
+                if (!role_wait(&S.full[s], nullptr, par, 30, k, 4, WS_NSW, fw == 0)) break;
                 const u32 t = S.tile[s];
                 if (t >= A.n_tiles) break;
                 stamp(k, 0);
-                scan(s, t);
+                scan(s, t, k);
                 stamp(k, 1);
             }
         } else {
             u32 ended = 0;
             for (u32 k = 0;; k++) {
                 const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
-                if (!wait_on(&S.full[s], par, 32, k)) break;
+                // (an end marker's `scanned` never completes: look at the tile id first)
+                if (!role_wait(&S.full[s], nullptr, par, 32, k, 5, WS_NMW, fw == WS_NSW)) break;
                 const u32 t = S.tile[s];
                 if (t >= A.n_tiles) {                       // end markers: wake every probe group, then leave
                     __syncwarp();
@@ -1051,9 +1212,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     if (++ended == WS_NPG) break;
                     continue;
                 }
-                if (!wait_on(&S.resolved[s], par, 31, k)) break;
+                if (!role_wait(&S.scanned[s], nullptr, par, 33, k, 5, WS_NMW, fw == WS_NSW)) break;
                 stamp(k, 2);
-                mask(s, t);
+                mask(s, t, k);
                 stamp(k, 3);
             }
         }
@@ -1063,7 +1224,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         for (u32 k = pg;; k += WS_NPG) {
             const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
             stamp(k, 0);
-            if (!wait_on(&S.ready[s], par, 40, k)) break;
+            if (!role_wait(&S.ready[s], nullptr, par, 40, k, 2 + pg, WS_NPW, pw == 0)) break;
             stamp(k, 1);
             const u32 t = S.tile[s];
             if (t >= A.n_tiles) break;
@@ -1285,6 +1446,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         a.tile_bytes = tile_bytes; a.n_tiles = n_tiles; a.tile_desc = desc;
         a.cand_count = counters + 0; a.total_newlines = counters + 1;
         a.tile_counter = (u32 *)(counters + 2); a.flags = (u32 *)(counters + 2) + 1;
+        a.count_counter = (u32 *)(counters + 3);
         a.bitmap = ctx->d_bitmap; a.bitmap_bytes = ctx->bitmap_words * 4; a.ptab = ctx->d_ptab; a.two_hash = ctx->kp.mw >= 22 ? 1u : 0u;
         a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp; a.trace = (u64 *)ctx->d_trace; a.wd = counters + 8;
         u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;

@@ -20,18 +20,16 @@ sk.fastq_koc_device(d, nbytes)
 lib.mk_debug_set_trace(sk._h, None)
 t = tr.cpu().numpy().reshape(48, 32, 4)
 t0 = t[20, 0, 0]
-NRES, NSW, NMW, NPG, NPW = [int(x) for x in os.environ.get("WS", "2,6,6,2,7").split(",")]
-R0 = 1 + NRES
+NCW, NSW, NMW, NPG, NPW = [int(x) for x in os.environ.get("WS", "4,6,6,2,7").split(",")]
+R0 = 2 + NCW
 for k_ in range(20, 26):
     r = t[k_]
     print("tile k=%d" % k_)
-    print("  loader   issue@%6d" % (r[0, 0] - t0))
-    rw = 1 + k_ % NRES
-    print("  resolver%d start@%6d scanned@%6d resolved@%6d" % ((rw - 1,) + tuple(r[rw, i] - t0 for i in range(3))))
+    print("  loader   freed@%6d issued@%6d" % tuple(r[0, i] - t0 for i in range(2)))
     for w in (R0, R0 + NSW - 1):
         print("  scan%d    full@%6d scan_done@%6d" % ((w - R0,) + tuple(r[w, i] - t0 for i in range(2))))
     for w in (R0 + NSW, R0 + NSW + NMW - 1):
-        print("  mask%d    resolved@%6d mask_done@%6d" % ((w - R0 - NSW,) + tuple(r[w, i] - t0 for i in (2, 3))))
+        print("  mask%d    start@%6d mask_done@%6d" % ((w - R0 - NSW,) + tuple(r[w, i] - t0 for i in (2, 3))))
     g = k_ % NPG
     b = R0 + NSW + NMW + g * NPW
     for w in (b, b + NPW - 1):

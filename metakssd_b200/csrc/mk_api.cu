@@ -133,18 +133,20 @@ extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int 
     K.ptab_mask = (u32)(tcap - 1);
     std::vector<u64> ptab(tcap, 0);
     u32 bm_words;
-    if (K.mw >= 20) bm_words = 1u << 15;
-    else bm_words = 1u << (K.mw - 5);
+    if (K.mw >= 22) bm_words = 1u << MK_BLOOM_WBITS; // two-hash Bloom filter
+    else bm_words = 1u << (K.mw - 5);               // exact bitmap (128 KB at mw = 20)
     if (bm_words < 4) bm_words = 4;
     std::vector<u32> bitmap(bm_words, 0);
-    // mw >= 22: two-hash Bloom filter in 2^20 bits (first hash: window bits 2..21, second hash:
-    // bits {0,1,6..23}); mw <= 20: exact bitmap.  Mirrors probe_block()/second_hash_hit().
+    // mw >= 22: two-hash Bloom filter in 2^(MK_BLOOM_WBITS+5) bits; mw <= 20: exact bitmap.  Mirrors probe_block()/second_hash_hit().
     auto set_bit = [&](u64 q) {
         u32 word, bit;
         if (K.mw >= 22) {
-            word = (u32)(q >> 2) & 0x7FFFu; bit = (u32)(q >> 17) & 31u;
+            const u32 wm = (1u << MK_BLOOM_WBITS) - 1u;
+            word = (u32)(q >> 2) & wm; bit = (u32)(q >> (MK_BLOOM_WBITS + 2)) & 31u;
             bitmap[word] |= 1u << (31 - bit);
-            word = (u32)(q >> 6) & 0x7FFFu; bit = ((u32)(q >> 21) & 7u) | (((u32)q & 3u) << 3);
+            word = (u32)(q >> 6) & wm;
+            bit = ((u32)(q >> (6 + MK_BLOOM_WBITS)) & ((1u << MK_BLOOM_TOPBITS) - 1u)) |
+                  (((u32)q & ((1u << (5 - MK_BLOOM_TOPBITS)) - 1u)) << MK_BLOOM_TOPBITS);
             bitmap[word] |= 1u << (31 - bit);
         } else {
             word = (u32)(q & ((1ull << (K.mw - 5)) - 1)); bit = (u32)(q >> (K.mw - 5)) & 31u;

@@ -12,6 +12,12 @@
 typedef unsigned long long u64;
 typedef unsigned int u32;
 
+// two-hash Bloom filter over the pass set (inner windows of 22+ bits): 2^MK_BLOOM_WBITS 32-bit words.
+// 15 = 128 KB (fewer first-level false positives, 6-stage ring), 14 = 64 KB (10-stage ring)
+#ifndef MK_BLOOM_WBITS
+#define MK_BLOOM_WBITS 15
+#endif
+#define MK_BLOOM_TOPBITS (24 - 6 - MK_BLOOM_WBITS)   // window bits above the second hash's word index
 #define MK_HALO 32            // bytes of left context staged in front of every text tile
 #define MK_MAX_TILE 24576     // tile-proper bytes (multiple of 64); three stages fit beside the bitmap
 #ifndef MK_STREAM_THREADS

@@ -60,7 +60,7 @@ __device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 #ifndef MK_WAIT_HINT
-#define MK_WAIT_HINT 0x989680   // try_wait suspend-time hint (ns): waiting warps sleep in hardware instead of polling
+#define MK_WAIT_HINT 2000       // try_wait suspend-time hint (ns); small enough that the poll-count watchdog still fires within seconds
 #endif
 __device__ __forceinline__ u32 mbar_try_wait(u64 *bar, u32 parity)
 {
@@ -251,7 +251,7 @@ __device__ __forceinline__ u32 take_bits(const u32 (&A)[4])
 template <int ROTOFF, u32 WORDMASK, int J>
 __device__ __forceinline__ void probe_one(const u32 (&A)[4], const u32 *bm, u32 &hits)
 {
-    constexpr int NEEDV = (WORDMASK == 0x1FFFCu) ? 17 : (WORDMASK == 0x1FFCu ? 13 : 9);
+    constexpr int NEEDV = ROTOFF;     // bits 0..1 of v are masked off, bits 2..ROTOFF-1 index the word
     u32 v = take_bits<2 * J, NEEDV>(A);
     u32 r = take_bits<2 * J + ROTOFF, 5>(A);
     u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + (v & WORDMASK));
@@ -293,16 +293,17 @@ __device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, in
     return __brev(hits);
 }
 
-// Second hash of the two-hash Bloom filter (inner windows of 22 bits or more): uses window bits
-// {0,1} and {6..23}, i.e. includes the four bits the first hash ignores.  Must mirror set_bit() in
+// Second hash of the two-hash Bloom filter (inner windows of 22 bits or more): word from window bits
+// 6..5+MK_BLOOM_WBITS, bit from the window bits above them and the lowest bits (the first hash uses
+// bits 2..6+MK_BLOOM_WBITS).  Must mirror set_bit() in
 // mk_api.cu.
 __device__ __forceinline__ bool second_hash_hit(const u32 (&A)[4], u32 j, const u32 *bm)
 {
     u32 lo = j < 16 ? A[0] : A[1];
     u32 hi = j < 16 ? A[1] : A[2];
     u32 v = __funnelshift_r(lo, hi, (2 * j) & 31);
-    u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + ((v >> 4) & 0x1FFFCu));
-    u32 bit = ((v >> 21) & 7u) | ((v & 3u) << 3);
+    u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + ((v >> 4) & (((1u << MK_BLOOM_WBITS) - 1u) << 2)));
+    u32 bit = ((v >> (6 + MK_BLOOM_WBITS)) & ((1u << MK_BLOOM_TOPBITS) - 1u)) | ((v & ((1u << (5 - MK_BLOOM_TOPBITS)) - 1u)) << MK_BLOOM_TOPBITS);
     return (word >> (31u - bit)) & 1u;
 }
 
@@ -752,12 +753,19 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 #define WS_G 4          // tiles per ticket (consecutive tiles of one CTA)
 #endif
 #define WS_ROLE0 (2 + WS_NCW)   // first front-end warp (0 = loader, 1 = resolver, then the count warps)
+#define WS_SCT (WS_NSW / WS_NPG)   // warps per scan team
+#define WS_MKT (WS_NMW / WS_NPG)   // warps per mask team
 #define WS_THREADS (32 * (WS_ROLE0 + WS_NFW + WS_NPG * WS_NPW))
+static_assert(WS_NSW % WS_NPG == 0 && WS_NMW % WS_NPG == 0, "teams");
+static_assert(WS_G == 4 && WS_TILE < 16384, "descriptor packing");
 #ifndef WS_PF_DIST
 #define WS_PF_DIST 3    // L2 prefetch distance in units of gridDim tiles
 #endif
 #define WS_TBUF (MK_HALO + WS_TILE + 96)
 
+#ifndef WS_HITBUF
+#define WS_HITBUF 94     // hits buffered per tile (~14 expected at L3K11); the rest goes straight to global memory
+#endif
 struct WsStage {
     u32 nlm[WS_BLK];             // newline mask of each block; the mask warps overwrite it in place with
                                  // the block's sequence-byte mask (same index, same thread)
@@ -765,17 +773,20 @@ struct WsStage {
     uint16_t items[WS_BLK];
     u32 ctot[WS_CHUNK];
     u32 cpre[WS_CHUNK];
+    u32 nhit, pfin, pcur;        // hits of this tile so far, rounds completed, next round of items
+    uint16_t hit[WS_HITBUF];     // tile offsets of the hits (flushed with one global atomic per tile)
 };
+template <int NS>
 struct WsSmem {
-    WsStage st[WS_NS];
-    u64 full[WS_NS], scanned[WS_NS], ready[WS_NS], done[WS_NS];
+    WsStage st[NS];
+    u64 full[NS], scanned[NS], ready[NS], done[NS];
     u64 gready[2], gfree[2];     // group mailbox resolver -> loader
-    u64 gq_P[2];
+    u64 gq_P[2][4];              // newlines before each tile of the group
     u32 gq_g[2];
-    u32 cticket, csum;           // count team: current group ticket, its newline count so far
+    u32 cticket, csum[2];        // count team: current group ticket, its packed per-tile newline counts so far
     u32 abort;                   // a leader's wait gave up: the whole role leaves
-    u64 Pn[2 * WS_NS];           // newlines before the k-th tile of this CTA (index k % (2 NS))
-    u32 tile[WS_NS], n_items[WS_NS], scnt[WS_NS], tot[WS_NS];
+    u64 Pn[2 * NS];           // newlines before the k-th tile of this CTA (index k % (2 NS))
+    u32 tile[NS], n_items[NS], scnt[NS], tot[NS];
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p, u32 bytes)
@@ -807,7 +818,7 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int ROTOFF, u32 WORDMASK, int PREW, bool RAW>
+template <int ROTOFF, u32 WORDMASK, int PREW, bool RAW, int NS>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_constant__ StreamArgs A)
 {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -816,7 +827,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
     const u32 bm_bytes = (A.bitmap_bytes + 127u) & ~127u;
     u32 *bm = reinterpret_cast<u32 *>(smem);
     uint8_t *tbuf = smem + bm_bytes;
-    WsSmem &S = *reinterpret_cast<WsSmem *>(tbuf + WS_NS * WS_TBUF);
+    static_assert(NS % WS_NPG == 0, "teams");
+    WsSmem<NS> &S = *reinterpret_cast<WsSmem<NS> *>(tbuf + NS * WS_TBUF);
 
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(A.bitmap);
@@ -824,15 +836,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         for (u32 i = tid; i < A.bitmap_bytes / 16; i += WS_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        for (int s = 0; s < WS_NS; s++) {
+        for (int s = 0; s < NS; s++) {
             mbar_init(&S.full[s], 1);
-            mbar_init(&S.scanned[s], WS_NSW);
-            mbar_init(&S.ready[s], WS_NMW);
+            mbar_init(&S.scanned[s], WS_SCT);
+            mbar_init(&S.ready[s], WS_MKT);
+#ifdef WS_PROBE_DYNAMIC
+            mbar_init(&S.done[s], WS_NPG * WS_NPW);
+#else
             mbar_init(&S.done[s], WS_NPW);
-            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0; S.tot[s] = 0;
+#endif
+            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0; S.tot[s] = 0; S.st[s].nhit = 0; S.st[s].pfin = 0; S.st[s].pcur = 0;
         }
         for (int q = 0; q < 2; q++) { mbar_init(&S.gready[q], 1); mbar_init(&S.gfree[q], 1); }
-        S.cticket = 0; S.csum = 0; S.abort = 0;
+        S.cticket = 0; S.csum[0] = 0; S.csum[1] = 0; S.abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();   // the only block-wide barrier of the kernel
@@ -880,17 +896,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         // refilled without any global round trip.
         if (lane == 0) {
             u32 ended = 0, j = 0, g = 0, i = 0, cnt = 0;
-            u64 P = 0;
+            u64 P[4] = {0, 0, 0, 0};
             bool finished = false;
             for (u32 k = 0;; k++) {
-                const u32 s = k % WS_NS, v = k / WS_NS;
+                const u32 s = k % NS, v = k / NS;
                 if (v > 0 && !wait_on(&S.done[s], (v - 1) & 1u, 10, k)) break;
                 stamp(k, 0);
                 if (!finished && i == cnt) {            // next group of this CTA
                     const u32 slot = j & 1u;
                     if (!wait_on(&S.gready[slot], (j >> 1) & 1u, 11, k)) break;
                     g = S.gq_g[slot];
-                    P = S.gq_P[slot];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) P[q] = S.gq_P[slot][q];
                     mbar_arrive(&S.gfree[slot]);
                     j++;
                     if (g >= n_groups) finished = true;
@@ -902,13 +919,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 }
                 const u32 t = finished ? 0xFFFFFFFFu : g * WS_G + i;
                 S.n_items[s] = 0;
+                S.st[s].pcur = 0; S.st[s].pfin = 0; S.st[s].nhit = 0;
                 S.tile[s] = t;
                 if (t >= A.n_tiles) {       // end marker: one per probe group, in consecutive ring slots
                     mbar_arrive(&S.full[s]);
                     if (++ended == WS_NPG) break;
                     continue;
                 }
-                if (i == 0) S.Pn[k % (2 * WS_NS)] = A.line_base + P;   // (later tiles of the group: scan finisher)
+                S.Pn[k % (2 * NS)] = A.line_base + P[i & 3u];
                 i++;
                 stamp(k, 1);
                 const u32 tb = tile_len(t);
@@ -944,8 +962,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             if (lane == 0) g = atomicAdd(A.tile_counter, 1u);
             g = __shfl_sync(0xffffffffu, g, 0);
             u64 P = 0;
+            u32 c4[4] = {0, 0, 0, 0};
             if (!RAW && g < n_groups) {
-                u32 sum = 0, own = 0;
+                u32 sum = 0, own_lo = 0, own_hi = 0;
                 bool good = true;
                 for (long long i0 = prev_g + 1; i0 <= (long long)g; i0 += 256) {
                     u32 lo[8], hi[8];
@@ -963,20 +982,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                             __nanosleep(200);
                             ld_volatile_v2(&A.tile_desc[idx], lo[q], hi[q]);
                         }
-                        if (idx == (long long)g) own = lo[q]; else sum += lo[q];
+                        if (idx == (long long)g) { own_lo = lo[q]; own_hi = hi[q]; }
+                        else sum += (lo[q] & 0xFFFFu) + (lo[q] >> 16) + (hi[q] & 0xFFFFu) + ((hi[q] >> 16) & 0x3FFFu);
                     }
                 }
                 sum = __reduce_add_sync(0xffffffffu, sum);
-                own = __reduce_add_sync(0xffffffffu, own);
+                own_lo = __reduce_add_sync(0xffffffffu, own_lo);
+                own_hi = __reduce_add_sync(0xffffffffu, own_hi);
                 if (!__all_sync(0xffffffffu, good)) break;
                 P = run_incl + sum;
-                run_incl = P + own;
+                c4[0] = own_lo & 0xFFFFu; c4[1] = own_lo >> 16; c4[2] = own_hi & 0xFFFFu; c4[3] = (own_hi >> 16) & 0x3FFFu;
+                run_incl = P + c4[0] + c4[1] + c4[2] + c4[3];
                 prev_g = (long long)g;
                 if (lane == 0 && g == n_groups - 1) *A.total_newlines = A.line_base + run_incl;
             }
             if (lane == 0) {
                 S.gq_g[slot] = g;
-                S.gq_P[slot] = P;
+                u64 p = P;
+#pragma unroll
+                for (int i = 0; i < 4; i++) { S.gq_P[slot][i] = p; p += c4[i]; }
                 __threadfence_block();
                 mbar_arrive(&S.gready[slot]);
             }
@@ -1007,7 +1031,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * WS_NCW) : "memory");
                 const u32 c = S.cticket;
                 if (c >= n_groups) break;
-                u32 gtotal = 0;
                 for (u32 i = cw; i < (u32)WS_G; i += WS_NCW) {
                     const u32 t = c * WS_G + i;
                     if (t >= A.n_tiles) break;
@@ -1064,24 +1087,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     total = (total & 0xFFFFu) + (total >> 16);
                     total = __reduce_add_sync(0xffffffffu, total);
                     if (lane == 0 && total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
-                    gtotal += total;
+                    // descriptor = four 14-bit per-tile counts at bit 16 i (a tile has < 2^14 bytes)
+                    if (lane == 0 && total) atomicAdd(&S.csum[i >> 1], total << (16u * (i & 1u)));
                 }
-                if (lane == 0 && gtotal) atomicAdd(&S.csum, gtotal);
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * WS_NCW) : "memory");
                 if (cw == 0 && lane == 0) {
-                    st_volatile_u64(&A.tile_desc[c], (1ull << 62) | (u64)S.csum);
-                    S.csum = 0;     // (the team adds to it again only after the next barrier)
+                    st_volatile_u64(&A.tile_desc[c], (1ull << 62) | ((u64)S.csum[1] << 32) | (u64)S.csum[0]);
+                    S.csum[0] = 0; S.csum[1] = 0;   // (the team adds to them again only after the next barrier)
                 }
             }
         }
     } else if (wid < WS_ROLE0 + WS_NFW) {
         // ======================= front end: scan warps and mask warps ==============================
+        // Each role works as WS_NPG teams on alternating tiles (team = k % WS_NPG), so that a warp has
+        // WS_NPG tile periods for its share of a tile.
         const u32 fw = wid - WS_ROLE0;
+        const bool is_scan = fw < WS_NSW;
+        const u32 team = (is_scan ? fw : fw - WS_NSW) / (is_scan ? WS_SCT : WS_MKT);
+        const u32 member = (is_scan ? fw : fw - WS_NSW) % (is_scan ? WS_SCT : WS_MKT);
         auto scan = [&](u32 s, u32 t, u32 k) {
             WsStage &G = S.st[s];
             uint8_t *tx = tbuf + s * WS_TBUF;
             const u32 tb = tile_len(t);
-            for (u32 c = fw; c < NCHUNK; c += WS_NSW) {
+            for (u32 c = member; c < NCHUNK; c += WS_SCT) {
                 const u32 off = c * 2048u + lane * 64u;        // my 64 bytes (two blocks)
                 if (t == 0 && c == 0 && lane < MK_HALO / 4) reinterpret_cast<u32 *>(tx)[lane] = 0;
                 if (off + 64u > tb && off < TB) {               // blank what lies outside the text
@@ -1129,7 +1157,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             u32 old = 0;
             if (lane == 0) { __threadfence_block(); old = atomicAdd(&S.scnt[s], 1u); }
             old = __shfl_sync(0xffffffffu, old, 0);
-            if (old == WS_NSW - 1 && !RAW) {
+            if (old == WS_SCT - 1 && !RAW) {
                 __threadfence_block();
                 u32 v = lane < NCHUNK ? G.ctot[lane] : 0;
                 u32 incl = v;
@@ -1139,18 +1167,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     if (lane >= (u32)o) incl += x;
                 }
                 if (lane < NCHUNK) G.cpre[lane] = incl - v;
-                // later tiles of a group take their line number from the tile before them
-                if (lane == 15 && (t + 1) % WS_G != 0) S.Pn[(k + 1) % (2 * WS_NS)] = S.Pn[k % (2 * WS_NS)] + incl;
             }
-            if (old == WS_NSW - 1 && lane == 0) S.scnt[s] = 0;
+            if (old == WS_SCT - 1 && lane == 0) S.scnt[s] = 0;
             __syncwarp();
             if (lane == 0) { __threadfence_block(); mbar_arrive(&S.scanned[s]); }
         };
         auto mask = [&](u32 s, u32 t, u32 k) {
             WsStage &G = S.st[s];
             const u32 tb = tile_len(t);
-            const u32 P = RAW ? 0u : (u32)S.Pn[k % (2 * WS_NS)];
-            for (u32 u = fw - WS_NSW; u < NMUNIT; u += WS_NMW) {
+            const u32 P = RAW ? 0u : (u32)S.Pn[k % (2 * NS)];
+            for (u32 u = member; u < NMUNIT; u += WS_MKT) {
                 u32 pm[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -1187,42 +1213,99 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             __syncwarp();
             if (lane == 0) { __threadfence_block(); mbar_arrive(&S.ready[s]); }
         };
-        if (fw < WS_NSW) {
-            // scan warps never wait for a look-back: newline counts of claimed tiles are published as
-            // soon as their text has landed, which is what keeps every CTA's resolver fast
-            for (u32 k = 0;; k++) {
-                const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
-                if (!role_wait(&S.full[s], nullptr, par, 30, k, 4, WS_NSW, fw == 0)) break;
+        if (is_scan) {
+            for (u32 k = team;; k += WS_NPG) {
+                const u32 s = k % NS, par = (k / NS) & 1u;
+                if (!role_wait(&S.full[s], nullptr, par, 30, k, 4 + team, WS_SCT, member == 0)) break;
                 const u32 t = S.tile[s];
-                if (t >= A.n_tiles) break;
+                if (t >= A.n_tiles) break;                  // (one end marker per team)
                 stamp(k, 0);
                 scan(s, t, k);
                 stamp(k, 1);
             }
         } else {
-            u32 ended = 0;
-            for (u32 k = 0;; k++) {
-                const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
+            for (u32 k = team;; k += WS_NPG) {
+                const u32 s = k % NS, par = (k / NS) & 1u;
                 // (an end marker's `scanned` never completes: look at the tile id first)
-                if (!role_wait(&S.full[s], nullptr, par, 32, k, 5, WS_NMW, fw == WS_NSW)) break;
+                if (!role_wait(&S.full[s], nullptr, par, 32, k, 4 + WS_NPG + team, WS_MKT, member == 0)) break;
                 const u32 t = S.tile[s];
-                if (t >= A.n_tiles) {                       // end markers: wake every probe group, then leave
+                if (t >= A.n_tiles) {                       // end marker: wake this team's probe group, then leave
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.ready[s]);
-                    if (++ended == WS_NPG) break;
-                    continue;
+                    break;
                 }
-                if (!role_wait(&S.scanned[s], nullptr, par, 33, k, 5, WS_NMW, fw == WS_NSW)) break;
+                if (!role_wait(&S.scanned[s], nullptr, par, 33, k, 4 + WS_NPG + team, WS_MKT, member == 0)) break;
                 stamp(k, 2);
                 mask(s, t, k);
                 stamp(k, 3);
             }
         }
     } else {
+#ifdef WS_PROBE_DYNAMIC
+        // ======================= probe ==========================================================
+        // Every probe warp visits every tile and pulls rounds of 32 items from it; a warp that finds a
+        // tile exhausted moves on to the next one, so the warps spread over the tiles in flight.
+        for (u32 k = 0;; k++) {
+            const u32 s = k % NS, par = (k / NS) & 1u;
+            stamp(k, 0);
+            if (!wait_on(&S.ready[s], par, 40, k)) break;
+            stamp(k, 1);
+            const u32 t = S.tile[s];
+            if (t >= A.n_tiles) break;
+            WsStage &G = S.st[s];
+            const uint8_t *tx = tbuf + s * WS_TBUF;
+            const u64 T = (u64)t * TB;
+            const u32 n = S.n_items[s];
+            const u32 rounds = (n + 31u) >> 5;
+            // (visiting a tile that has no round left costs two shared-memory loads and the arrive)
+            // (lane 0's view, broadcast: lanes reading the cursor at different times would split the warp)
+            while (__shfl_sync(0xffffffffu, *(volatile u32 *)&G.pcur, 0) < rounds) {
+                u32 r = 0;
+                if (lane == 0) r = atomicAdd(&G.pcur, 1u);
+                r = __shfl_sync(0xffffffffu, r, 0);
+                if (r >= rounds) break;
+                const u32 it = r * 32u + lane;
+                if (it < n) {
+                    const u32 b = G.items[it];
+                    u32 Aw[4];
+                    u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
+                    hits &= G.nlm[b];                       // sequence-byte mask by now
+                    while (hits) {
+                        u32 j = __ffs(hits) - 1;
+                        hits &= hits - 1;
+                        if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
+                        const u32 h = atomicAdd(&G.nhit, 1u);
+                        if (h < WS_HITBUF) G.hit[h] = (uint16_t)(32 * b + j);
+                        else emit_hit(A, T + 32 * b + j);
+                    }
+                }
+                __syncwarp();
+                // the warp that completes the tile's last round appends the buffered hits to the global list
+                u32 fin = 0;
+                if (lane == 0) { __threadfence_block(); fin = atomicAdd(&G.pfin, 1u); }
+                fin = __shfl_sync(0xffffffffu, fin, 0);
+                if (fin == rounds - 1) {
+                    __threadfence_block();
+                    const u32 nh = G.nhit < WS_HITBUF ? G.nhit : (u32)WS_HITBUF;
+                    if (nh) {
+                        u64 base = 0;
+                        if (lane == 0) base = atomicAdd((unsigned long long *)A.cand_count, (unsigned long long)nh);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        for (u32 i = lane; i < nh; i += 32)
+                            if (base + i < A.cand_cap) A.cand_pos[base + i] = T + G.hit[i];
+                    }
+                    __syncwarp();
+                }
+            }
+            stamp(k, 2);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.done[s]);   // (the loader resets the tile's cursors when it refills the stage)
+        }
+#else
         // ======================= probe ==========================================================
         const u32 pg = (wid - WS_ROLE0 - WS_NFW) / WS_NPW, pw = (wid - WS_ROLE0 - WS_NFW) % WS_NPW;
         for (u32 k = pg;; k += WS_NPG) {
-            const u32 s = k % WS_NS, par = (k / WS_NS) & 1u;
+            const u32 s = k % NS, par = (k / NS) & 1u;
             stamp(k, 0);
             if (!role_wait(&S.ready[s], nullptr, par, 40, k, 2 + pg, WS_NPW, pw == 0)) break;
             stamp(k, 1);
@@ -1251,6 +1334,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.done[s]);
         }
+#endif
     }
 }
 
@@ -1352,22 +1436,24 @@ extern "C" int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t 
 // ---- host driver -------------------------------------------------------------------------------
 typedef void (*stream_kernel_t)(const StreamArgs);
 
-template <int ROTOFF, u32 WORDMASK>
+template <int ROTOFF, u32 WORDMASK, int NS>
 static stream_kernel_t pick2_ws(int prew, bool raw)
 {
-    if (prew == 1) return raw ? k_stream_ws<ROTOFF, WORDMASK, 1, true> : k_stream_ws<ROTOFF, WORDMASK, 1, false>;
-    return raw ? k_stream_ws<ROTOFF, WORDMASK, 2, true> : k_stream_ws<ROTOFF, WORDMASK, 2, false>;
+    if (prew == 1) return raw ? k_stream_ws<ROTOFF, WORDMASK, 1, true, NS> : k_stream_ws<ROTOFF, WORDMASK, 1, false, NS>;
+    return raw ? k_stream_ws<ROTOFF, WORDMASK, 2, true, NS> : k_stream_ws<ROTOFF, WORDMASK, 2, false, NS>;
 }
+static int ws_stages(const KParams &kp) { return (kp.mw == 20 || (kp.mw >= 22 && MK_BLOOM_WBITS == 15)) ? 6 : 10; }
 static stream_kernel_t pick_kernel_ws(const KParams &kp, bool raw)
 {
-    if (kp.mw >= 20) return pick2_ws<17, 0x1FFFCu>(kp.prew, raw);
-    if (kp.mw == 16) return pick2_ws<13, 0x1FFCu>(kp.prew, raw);
-    if (kp.mw == 12) return pick2_ws<9, 0x1FCu>(kp.prew, raw);
+    if (kp.mw >= 22) return pick2_ws<MK_BLOOM_WBITS + 2, ((1u << MK_BLOOM_WBITS) - 1u) << 2, MK_BLOOM_WBITS == 15 ? 6 : 10>(kp.prew, raw);   // two-hash filter
+    if (kp.mw == 20) return pick2_ws<17, 0x1FFFCu, 6>(kp.prew, raw);    // 128 KB exact bitmap, 6 stages
+    if (kp.mw == 16) return pick2_ws<13, 0x1FFCu, 10>(kp.prew, raw);
+    if (kp.mw == 12) return pick2_ws<9, 0x1FCu, 10>(kp.prew, raw);
     return nullptr;
 }
-static size_t stream_smem_bytes_ws(u32 bitmap_bytes)
+static size_t stream_smem_bytes_ws(u32 bitmap_bytes, int ns)
 {
-    return ((bitmap_bytes + 127u) & ~127u) + (size_t)WS_NS * WS_TBUF + sizeof(WsSmem) + 64;
+    return ((bitmap_bytes + 127u) & ~127u) + (size_t)ns * WS_TBUF + (ns == 6 ? sizeof(WsSmem<6>) : sizeof(WsSmem<10>)) + 64;
 }
 
 template <int ROTOFF, u32 WORDMASK>
@@ -1378,7 +1464,8 @@ static stream_kernel_t pick2(int prew, bool raw)
 }
 static stream_kernel_t pick_kernel(const KParams &kp, bool raw)
 {
-    if (kp.mw >= 20) return pick2<17, 0x1FFFCu>(kp.prew, raw);
+    if (kp.mw >= 22) return pick2<MK_BLOOM_WBITS + 2, ((1u << MK_BLOOM_WBITS) - 1u) << 2>(kp.prew, raw);
+    if (kp.mw == 20) return pick2<17, 0x1FFFCu>(kp.prew, raw);
     if (kp.mw == 16) return pick2<13, 0x1FFCu>(kp.prew, raw);
     if (kp.mw == 12) return pick2<9, 0x1FCu>(kp.prew, raw);
     return nullptr;
@@ -1429,10 +1516,10 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     CKR(mk_scratch(ctx, SB_TILE_DESC, (size_t)n_tiles, &desc));
     CKR(mk_scratch(ctx, SB_COUNTERS, 16, &counters));
     // hit list capacity: members of S ∪ revcomp(S) (2 x pass rate) plus filter false positives
-    double rate = 2.0 * (double)kp.dim_end / (double)(1ull << (4 * kp.subk)) + 0.001;
+    double rate = 2.0 * (double)kp.dim_end / (double)(1ull << (4 * kp.subk)) + 0.003;
     if (rate > 1.0) rate = 1.0;
     u64 cap = (u64)((double)nbytes * rate * 0.75) + 65536;
-    size_t smem = ws ? stream_smem_bytes_ws(ctx->bitmap_words * 4) : stream_smem_bytes(ctx->bitmap_words * 4);
+    size_t smem = ws ? stream_smem_bytes_ws(ctx->bitmap_words * 4, ws_stages(kp)) : stream_smem_bytes(ctx->bitmap_words * 4);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
     for (int attempt = 0; attempt < 2; attempt++) {

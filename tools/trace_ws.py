@@ -26,11 +26,24 @@ for k_ in range(20, 26):
     r = t[k_]
     print("tile k=%d" % k_)
     print("  loader   freed@%6d issued@%6d" % tuple(r[0, i] - t0 for i in range(2)))
-    for w in (R0, R0 + NSW - 1):
+    tm = k_ % NPG
+    SCT, MKT = NSW // NPG, NMW // NPG
+    for w in (R0 + tm * SCT, R0 + tm * SCT + SCT - 1):
         print("  scan%d    full@%6d scan_done@%6d" % ((w - R0,) + tuple(r[w, i] - t0 for i in range(2))))
-    for w in (R0 + NSW, R0 + NSW + NMW - 1):
+    for w in (R0 + NSW + tm * MKT, R0 + NSW + tm * MKT + MKT - 1):
         print("  mask%d    start@%6d mask_done@%6d" % ((w - R0 - NSW,) + tuple(r[w, i] - t0 for i in (2, 3))))
     g = k_ % NPG
     b = R0 + NSW + NMW + g * NPW
     for w in (b, b + NPW - 1):
         print("  probe%d.%d start@%6d ready@%6d probed@%6d" % ((g, w - b) + tuple(r[w, i] - t0 for i in range(3))))
+if os.environ.get("COMPACT"):
+    print("role timelines (per tile k: wait-start, go, done) relative to first stamp")
+    for name, w, sl in (("loader", 0, (0, 1, 1)), ("scanT0", R0, (0, 0, 1)), ("scanT1", R0 + SCT, (0, 0, 1)),
+                        ("maskT0", R0 + NSW, (2, 2, 3)), ("maskT1", R0 + NSW + MKT, (2, 2, 3)),
+                        ("probe0", R0 + NSW + NMW, (0, 1, 2)), ("probe1", R0 + NSW + NMW + NPW, (0, 1, 2))):
+        line = []
+        for k_ in range(16, 40):
+            r = t[k_, w]
+            if r[sl[2]] == 0: continue
+            line.append("k%d:%d/%d/%d" % (k_, r[sl[0]] - t0, r[sl[1]] - t0, r[sl[2]] - t0))
+        print(name, " ".join(line))

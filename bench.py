@@ -157,16 +157,21 @@ def run_ours(args):
 
     lib_stream = torch.cuda.ExternalStream(sk.cuda_stream(), device=dev)
 
-    def composite(sketch):
+    # `value` leg: everything the step reads is resident in HBM (FASTQ text and MarkerDB);
+    # `e2e` leg: host buffers, the MarkerDB is uploaded with every step like the reference re-reads it
+    if rank == 0:
+        sk.load_markerdb(mdb.comp)
+
+    def composite(sketch, resident):
         qry = [(sketch.codes[c], sketch.counts[c]) for c in range(len(sketch.codes))]
-        stats = sk.composite(mdb.comp, qry)
+        stats = sk.composite(None if resident else mdb.comp, qry)
         return M.composite_tsv("reads.fq", mdb.names, stats)
 
     def step_device():
         if world == 1:
-            return composite(sk.fastq_koc_device(d_text, nbytes))
+            return composite(sk.fastq_koc_device(d_text, nbytes), True)
         s = D.sketch_sharded(sk, d_text, nbytes, pos_base, 0, rank == world - 1)
-        return composite(s) if rank == 0 else None
+        return composite(s, True) if rank == 0 else None
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -216,12 +221,12 @@ def run_ours(args):
 
         def step_host():
             if world == 1:
-                return composite(sk.fastq_koc_host(h_text))
+                return composite(sk.fastq_koc_host(h_text), False)
             # multi-GPU: the shard goes through the same host-buffer upload, then the sharded path
             d_text[:e_nbytes].copy_(h_text, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
             s = D.sketch_sharded(sk, d_text, e_nbytes, pos_base, 0, rank == world - 1)
-            return composite(s) if rank == 0 else None
+            return composite(s, False) if rank == 0 else None
 
         e_steps = max(2, min(args.steps, 3))
         ms_e, tsv_e = timed(step_host, e_steps, 1)

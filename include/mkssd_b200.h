@@ -133,6 +133,15 @@ int mk_composite_begin(mk_ctx *ctx, int n_species);
 int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, int n_species,
                            const uint32_t *qry_codes, const uint16_t *qry_counts, uint64_t qry_lo,
                            uint64_t qry_hi);
+/* Resident MarkerDB (serving many samples against one database): mk_markerdb_load() uploads
+ * component `component` once and keeps it on the device; mk_composite_component_resident() is
+ * mk_composite_component() against that copy.  The reference re-reads the MarkerDB from disk on
+ * every `composite` run (command_composite.c:500-530); this is the same intersection without the
+ * repeated transfer.  mk_markerdb_unload() (or mk_ctx_destroy) releases the copies. */
+int mk_markerdb_load(mk_ctx *ctx, int component, const uint32_t *ref_codes, const uint64_t *ref_index, int n_species);
+int mk_markerdb_unload(mk_ctx *ctx);
+int mk_composite_component_resident(mk_ctx *ctx, int component, const uint32_t *qry_codes,
+                                    const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi);
 /* Per-species order statistics over the accumulated hits, the integers the reference prints
  * (command_composite.c:598-624); the two float ratios are sum/n and lastsum/lastn. */
 typedef struct mk_species_stat {

@@ -84,7 +84,8 @@ EXPORTS = [
     "mk_strerror", "mk_last_error", "mk_device_count", "mk_ctx_create", "mk_ctx_destroy", "mk_ctx_info",
     "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
     "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
-    "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_fastq_partial_device",
+    "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
+    "mk_composite_component_resident", "mk_fastq_partial_device",
     "mk_runs_finalize_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
@@ -127,6 +128,9 @@ def load():
     L.mk_composite_begin.argtypes = [vp, i32]
     L.mk_composite_component.argtypes = [vp, vp, vp, i32, vp, vp, u64, u64]
     L.mk_composite_stats.argtypes = [vp, vp]
+    L.mk_markerdb_load.argtypes = [vp, i32, vp, vp, i32]
+    L.mk_markerdb_unload.argtypes = [vp]
+    L.mk_composite_component_resident.argtypes = [vp, i32, vp, vp, u64, u64]
     L.mk_composite_hits.argtypes = [vp, C.POINTER(C.POINTER(C.POINTER(C.c_int32)))]
     L.mk_fastq_partial_device.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
     L.mk_runs_finalize_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkSketch)]
@@ -340,12 +344,32 @@ class Sketcher:
         return _take_sketch(sk, False)
 
     # -- composite
+    def load_markerdb(self, ref_comp):
+        """Keep a MarkerDB (per component: codes uint32[], index uint64[S+1]) resident on the device;
+        composite(None, qry) then intersects against it without re-uploading."""
+        self._ck(self._L.mk_markerdb_unload(self._h))
+        self._mdb_species = int(ref_comp[0][1].size - 1)
+        self._mdb_components = len(ref_comp)
+        for c, (rc, ri) in enumerate(ref_comp):
+            rc = np.ascontiguousarray(rc, dtype=np.uint32)
+            ri = np.ascontiguousarray(ri, dtype=np.uint64)
+            self._ck(self._L.mk_markerdb_load(self._h, c, rc.ctypes.data, ri.ctypes.data, self._mdb_species))
+
     def composite(self, ref_comp, qry_comp, want_lists: bool = False):
         """ref_comp: per component (codes uint32[], index uint64[S+1]); qry_comp: per component
         (codes uint32[], counts uint16[]) of ONE query.  Returns the per-species stats array
         (structured: n,sum,lastsum,lastn,median,max) and, optionally, the raw hit lists."""
-        S = int(ref_comp[0][1].size - 1)
-        self._ck(self._L.mk_composite_begin(self._h, S))
+        if ref_comp is None:                      # resident MarkerDB (load_markerdb)
+            S = self._mdb_species
+            self._ck(self._L.mk_composite_begin(self._h, S))
+            for c, (qc, qa) in enumerate(qry_comp[:self._mdb_components]):
+                qc = np.ascontiguousarray(qc, dtype=np.uint32)
+                qa = np.ascontiguousarray(qa, dtype=np.uint16)
+                self._ck(self._L.mk_composite_component_resident(self._h, c, qc.ctypes.data, qa.ctypes.data, 0, qc.size))
+            ref_comp = ()
+        else:
+            S = int(ref_comp[0][1].size - 1)
+            self._ck(self._L.mk_composite_begin(self._h, S))
         for (rc, ri), (qc, qa) in zip(ref_comp, qry_comp):
             rc = np.ascontiguousarray(rc, dtype=np.uint32)
             ri = np.ascontiguousarray(ri, dtype=np.uint64)
@@ -452,14 +476,14 @@ def composite_tsv(qry_name: str, ref_names, stats) -> str:
     """species_coverage lines exactly as command_composite.c:582-624 prints them: species ordered
     by matched k-mers (descending, ties by index as glibc's stable qsort leaves them), stopping at
     the first with fewer than MIN_KM_S = 6; ratios are computed in float32 and printed with %f."""
-    order = np.argsort(-stats["n"].astype(np.int64), kind="stable")
-    lines = []
-    for s in order:
-        n = int(stats["n"][s])
-        if n < 6:
-            break
-        mean = np.float32(np.int32(stats["sum"][s])) / np.float32(n)
-        last = np.float32(np.int32(stats["lastsum"][s])) / np.float32(int(stats["lastn"][s]))
-        lines.append("%s\t%s\t%d\t%f\t%f\t%d\t%d\n" % (qry_name, ref_names[s], n, float(mean), float(last),
-                                                     int(stats["median"][s]), int(stats["max"][s])))
+    n_all = stats["n"].astype(np.int64)
+    order = np.argsort(-n_all, kind="stable")
+    sel = order[:int(np.count_nonzero(n_all >= 6))]          # a prefix of the descending order
+    n = n_all[sel]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        mean = stats["sum"][sel].astype(np.int32).astype(np.float32) / n.astype(np.float32)
+        last = stats["lastsum"][sel].astype(np.int32).astype(np.float32) / stats["lastn"][sel].astype(np.int64).astype(np.float32)
+    lines = ["%s\t%s\t%d\t%f\t%f\t%d\t%d\n" % (qry_name, ref_names[s], a, b, c, d, e)
+             for s, a, b, c, d, e in zip(sel.tolist(), n.tolist(), mean.tolist(), last.tolist(),
+                                         stats["median"][sel].tolist(), stats["max"][sel].tolist())]
     return "".join(lines)

@@ -185,6 +185,7 @@ extern "C" void mk_ctx_destroy(mk_ctx *ctx)
     if (ctx->d_bitmap) cudaFree(ctx->d_bitmap);
     if (ctx->d_ptab) cudaFree(ctx->d_ptab);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    mk_markerdb_unload(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -248,11 +249,15 @@ extern "C" int mk_fastq_koc_device(mk_ctx *ctx, const void *d_text, size_t nbyte
     memset(out, 0, sizeof(*out));
     CK(cudaSetDevice(ctx->device));
     u64 *cc = nullptr, *cp = nullptr, n_cand = 0;
+    MkPhaseClock pc(ctx->stream);
     CKR(mk_stream_fastq(ctx, (const uint8_t *)d_text, nbytes, 0, 0, false, &cc, &cp, &n_cand, nullptr));
+    pc.mark("stream+verify");
     long long keep_below = -1;
     if (nbytes) CKR(mk_tail_cut(ctx, (const uint8_t *)d_text, nbytes, &keep_below));
+    pc.mark("tail cut");
     ctx->pos_bits = bits_for((u64)nbytes);
     int rc = mk_finalize_candidates(ctx, cc, cp, n_cand, keep_below, nullptr, 1, true, out);
+    pc.mark("finalize");
     ctx->pos_bits = 64;
     if (rc != MK_OK) mk_sketch_free(out);
     return rc;

@@ -55,6 +55,13 @@ enum {
     SB_RUN_POS, SB_RUN_CNT, SB_NUM
 };
 
+struct ResidentComponent {         // one MarkerDB component kept on the device (mk_markerdb_load)
+    u32 *d_ref = nullptr;
+    u64 *d_index = nullptr;
+    u64 r = 0;
+    int n_species = 0;
+};
+
 struct mk_ctx {
     int device = 0;
     int sm_count = 0;
@@ -79,6 +86,25 @@ struct mk_ctx {
     u64 comp_nhits = 0;
     std::vector<int32_t> comp_lists_flat;
     std::vector<const int32_t *> comp_lists_ptr;
+    std::vector<ResidentComponent> mdb;
+};
+
+// Development aid (env MK_TIMING=1): host wall clock between phase marks, with a stream sync at
+// every mark, printed to stderr.
+#include <chrono>
+struct MkPhaseClock {
+    bool on;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point t;
+    MkPhaseClock(cudaStream_t s) : on(getenv("MK_TIMING") != nullptr), st(s) { if (on) { cudaStreamSynchronize(st); t = std::chrono::steady_clock::now(); } }
+    void mark(const char *what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mk timing] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
 };
 
 #define CK(call)                                                                                   \
@@ -96,6 +122,25 @@ struct mk_ctx {
         int r_ = (expr);                                                                           \
         if (r_ != MK_OK) return r_;                                                                \
     } while (0)
+
+// grow-only pinned host staging block (device -> host result copies run at full PCIe speed from it)
+static inline int mk_pinned(mk_ctx *ctx, size_t bytes, void **out)
+{
+    if (ctx->h_pinned_bytes < bytes) {
+        if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+        ctx->h_pinned = nullptr;
+        ctx->h_pinned_bytes = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&ctx->h_pinned, want);
+        if (e != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "cudaMallocHost(%zu): %s", want, cudaGetErrorString(e));
+            return MK_ERR_NOMEM;
+        }
+        ctx->h_pinned_bytes = want;
+    }
+    *out = ctx->h_pinned;
+    return MK_OK;
+}
 
 // grow-only device scratch
 template <class T>

@@ -78,11 +78,12 @@ extern "C" int mk_composite_begin(mk_ctx *ctx, int n_species)
     return MK_OK;
 }
 
-extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, int n_species,
-                                      const uint32_t *qry_codes, const uint16_t *qry_counts, uint64_t qry_lo,
-                                      uint64_t qry_hi)
+// One MarkerDB component against the query codes [qry_lo, qry_hi).  The MarkerDB side is either the
+// host arrays of the call (uploaded now) or a component made resident by mk_markerdb_load().
+static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, const u32 *res_ref,
+                               const u64 *res_index, u64 r, int n_species, const uint32_t *qry_codes,
+                               const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi)
 {
-    if (!ctx || !ref_index || n_species != ctx->comp_species || qry_hi < qry_lo) return MK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const u64 q = qry_hi - qry_lo;
     // the reference sizes its dictionary with nextPrime((int)(q / 0.6)); 0 or 1 make it divide by zero
@@ -90,7 +91,6 @@ extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, co
         snprintf(ctx->err, sizeof(ctx->err), "composite: query sketch has %llu codes", (unsigned long long)q);
         return MK_ERR_EMPTY_QUERY;
     }
-    const u64 r = ref_index[n_species];
     if (r == 0) return MK_OK;
     if (r >= 0xFFFFFFFFull || q >= 0x7FFFFFFFull) return MK_ERR_UNSUPPORTED;
     cudaEvent_t e0 = ctx->ev2, e1 = ctx->ev3;
@@ -98,8 +98,13 @@ extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, co
     u32 *d_ref, *d_qry, *d_flag, *d_val, *d_pos, *d_idx, *store_s, *store_c;
     u64 *d_index, *d_keys;
     uint16_t *d_qcnt;
-    CKR(mk_scratch(ctx, SB_C_REF, (size_t)r, &d_ref));
-    CKR(mk_scratch(ctx, SB_C_IDX, (size_t)n_species + 1, &d_index));
+    if (res_ref) {
+        d_ref = const_cast<u32 *>(res_ref);
+        d_index = const_cast<u64 *>(res_index);
+    } else {
+        CKR(mk_scratch(ctx, SB_C_REF, (size_t)r, &d_ref));
+        CKR(mk_scratch(ctx, SB_C_IDX, (size_t)n_species + 1, &d_index));
+    }
     CKR(mk_scratch(ctx, SB_C_QRY, (size_t)q, &d_qry));
     CKR(mk_scratch(ctx, SB_C_QCNT, (size_t)q, &d_qcnt));
     CKR(mk_scratch(ctx, SB_C_HITVAL, (size_t)2 * r, &d_flag));
@@ -131,11 +136,14 @@ extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, co
         store_s = (u32 *)ss.p;
         store_c = (u32 *)sc.p;
     }
-    CK(cudaMemcpyAsync(d_ref, ref_codes, (size_t)r * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_index, ref_index, (size_t)(n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if (!res_ref) {
+        CK(cudaMemcpyAsync(d_ref, ref_codes, (size_t)r * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_index, ref_index, (size_t)(n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->prof.h2d_bytes += r * 4 + (u64)(n_species + 1) * 8;
+    }
     CK(cudaMemcpyAsync(d_qry, qry_codes + qry_lo, (size_t)q * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_qcnt, qry_counts + qry_lo, (size_t)q * 2, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->prof.h2d_bytes += r * 4 + (u64)(n_species + 1) * 8 + q * 6;
+    ctx->prof.h2d_bytes += q * 6;
     CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(d_idx, 0xFF, (size_t)cap * 4, ctx->stream));
     k_cq_insert<<<(unsigned)((q + 255) / 256), 256, 0, ctx->stream>>>(d_qry, q, d_keys, d_idx, (u32)(cap - 1));
@@ -156,6 +164,59 @@ extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, co
     ctx->prof.composite_ms += ms;
     ctx->comp_nhits += nh;
     return MK_OK;
+}
+
+extern "C" int mk_composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, int n_species,
+                                      const uint32_t *qry_codes, const uint16_t *qry_counts, uint64_t qry_lo,
+                                      uint64_t qry_hi)
+{
+    if (!ctx || !ref_index || n_species != ctx->comp_species || qry_hi < qry_lo) return MK_ERR_ARG;
+    return composite_component(ctx, ref_codes, ref_index, nullptr, nullptr, ref_index[n_species], n_species, qry_codes,
+                               qry_counts, qry_lo, qry_hi);
+}
+
+// ---- resident MarkerDB: load once, intersect many samples ------------------------------------------
+extern "C" int mk_markerdb_load(mk_ctx *ctx, int component, const uint32_t *ref_codes, const uint64_t *ref_index,
+                                int n_species)
+{
+    if (!ctx || component < 0 || component >= 65536 || !ref_index || n_species <= 0) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if ((size_t)component >= ctx->mdb.size()) ctx->mdb.resize((size_t)component + 1);
+    ResidentComponent &m = ctx->mdb[(size_t)component];
+    if (m.d_ref) cudaFree(m.d_ref);
+    if (m.d_index) cudaFree(m.d_index);
+    m = ResidentComponent();
+    const u64 r = ref_index[n_species];
+    CK(cudaMalloc(&m.d_ref, (size_t)(r ? r : 1) * 4));
+    CK(cudaMalloc(&m.d_index, (size_t)(n_species + 1) * 8));
+    if (r) CK(cudaMemcpyAsync(m.d_ref, ref_codes, (size_t)r * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(m.d_index, ref_index, (size_t)(n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.h2d_bytes += r * 4 + (u64)(n_species + 1) * 8;
+    m.r = r;
+    m.n_species = n_species;
+    return MK_OK;
+}
+
+extern "C" int mk_markerdb_unload(mk_ctx *ctx)
+{
+    if (!ctx) return MK_ERR_ARG;
+    for (ResidentComponent &m : ctx->mdb) {
+        if (m.d_ref) cudaFree(m.d_ref);
+        if (m.d_index) cudaFree(m.d_index);
+    }
+    ctx->mdb.clear();
+    return MK_OK;
+}
+
+extern "C" int mk_composite_component_resident(mk_ctx *ctx, int component, const uint32_t *qry_codes,
+                                               const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi)
+{
+    if (!ctx || component < 0 || (size_t)component >= ctx->mdb.size() || qry_hi < qry_lo) return MK_ERR_ARG;
+    const ResidentComponent &m = ctx->mdb[(size_t)component];
+    if (!m.d_index || m.n_species != ctx->comp_species) return MK_ERR_ARG;
+    return composite_component(ctx, nullptr, nullptr, m.d_ref, m.d_index, m.r, m.n_species, qry_codes, qry_counts, qry_lo,
+                               qry_hi);
 }
 
 __global__ void __launch_bounds__(256)

@@ -322,6 +322,8 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
     CKR(mk_scratch(ctx, SB_R_PROBE, (size_t)n, &probe_i));
     k_gather_ranked<<<(unsigned)nb, 256, 0, ctx->stream>>>(sv, n, d_it_key, d_it_cnt, r_key, r_cnt);
     LAUNCH_COUNT(ctx);
+    MkPhaseClock pc(ctx->stream);
+    pc.mark("    (rank sort done)");
 
     // sparse slot map
     u64 scap = pow2_at_least(2 * n + 2);
@@ -359,14 +361,20 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
     LAUNCH_COUNT(ctx);
     CK(cudaGetLastError());
 
-    std::vector<u64> h_seg(nseg + 1);
-    std::vector<uint32_t> h_code(n);
-    std::vector<uint16_t> h_cnt(with_counts ? n : 0);
-    CK(cudaMemcpyAsync(h_seg.data(), seg_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(h_code.data(), out_code, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (with_counts) CK(cudaMemcpyAsync(h_cnt.data(), out_cnt, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    pc.mark("    slots+sort+emit");
+    // results come back through the context's pinned staging block
+    const size_t seg_bytes = ((size_t)(nseg + 1) * 8 + 15) & ~(size_t)15, code_bytes = ((size_t)n * 4 + 15) & ~(size_t)15;
+    void *stage = nullptr;
+    CKR(mk_pinned(ctx, seg_bytes + code_bytes + (size_t)n * 2, &stage));
+    u64 *h_seg = (u64 *)stage;
+    uint32_t *h_code = (uint32_t *)((char *)stage + seg_bytes);
+    uint16_t *h_cnt = (uint16_t *)((char *)stage + seg_bytes + code_bytes);
+    CK(cudaMemcpyAsync(h_seg, seg_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(h_code, out_code, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (with_counts) CK(cudaMemcpyAsync(h_cnt, out_cnt, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->prof.d2h_bytes += nseg * 8 + n * 4 + (with_counts ? n * 2 : 0);
+    pc.mark("    d2h");
     // empty segments inherit the start of the next non-empty one
     h_seg[nseg] = n;
     for (long long s = (long long)nseg - 1; s >= 0; s--)
@@ -381,11 +389,11 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
             s->n_total += m;
             s->codes[c] = (uint32_t *)malloc((size_t)(m ? m : 1) * 4);
             if (!s->codes[c]) return MK_ERR_NOMEM;
-            memcpy(s->codes[c], h_code.data() + lo, (size_t)m * 4);
+            memcpy(s->codes[c], h_code + lo, (size_t)m * 4);
             if (with_counts) {
                 s->counts[c] = (uint16_t *)malloc((size_t)(m ? m : 1) * 2);
                 if (!s->counts[c]) return MK_ERR_NOMEM;
-                memcpy(s->counts[c], h_cnt.data() + lo, (size_t)m * 2);
+                memcpy(s->counts[c], h_cnt + lo, (size_t)m * 2);
             }
         }
         if (s->n_total > I.hashlimit) {
@@ -403,9 +411,12 @@ int mk_finalize_candidates(mk_ctx *ctx, const u64 *d_cand_code, const u64 *d_can
     u64 *it_key, *it_pos, n_items;
     u32 *it_cnt;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    MkPhaseClock pc(ctx->stream);
     CKR(mk_reduce_candidates(ctx, d_cand_code, d_cand_pos, n_cand, keep_below, d_file_off, n_files, ctx->info.code_bits,
                              &it_key, &it_cnt, &it_pos, &n_items));
+    pc.mark("  accumulate");
     int rc = mk_order_and_emit(ctx, it_key, it_cnt, it_pos, n_items, n_files, with_counts, d_file_off != nullptr, out);
+    pc.mark("  order+emit+copy");
     cudaEventRecord(ctx->ev3, ctx->stream);
     cudaEventSynchronize(ctx->ev3);
     float ms = 0;

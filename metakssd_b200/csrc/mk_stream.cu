@@ -747,7 +747,7 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 #define WS_NCW 4        // count-ahead warps
 #endif
 #ifndef WS_WINDOW
-#define WS_WINDOW 3     // the count pass may run this many x gridDim tiles ahead of the load front
+#define WS_WINDOW 2     // the count pass may run this many x gridDim tiles ahead of the load front
 #endif
 #ifndef WS_G
 #define WS_G 4          // tiles per ticket (consecutive tiles of one CTA)

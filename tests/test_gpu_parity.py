@@ -222,6 +222,10 @@ def test_composite_matches_oracle(oracle, sk311):
     g = s.fastq_koc_host(S.fastq(0, 60000))
     stats2 = s.composite([(ref_codes, ref_index)], [(g.codes[0], g.counts[0])])
     assert composite_tsv("reads.fq", names, stats2) == want
+    # resident MarkerDB: same answer, repeatedly, without re-uploading the database
+    s.load_markerdb([(ref_codes, ref_index)])
+    for _ in range(2):
+        assert composite_tsv("reads.fq", names, s.composite(None, [(g.codes[0], g.counts[0])])) == want
 
 
 def test_composite_multi_component(oracle, lib_built, shuf):
@@ -238,7 +242,10 @@ def test_composite_multi_component(oracle, lib_built, shuf):
     want = oracle.composite(ref, names, q, "q.fq")
     with lib_built.Sketcher(perm, k, subk, L) as sk:
         stats = sk.composite(ref, q)
+        sk.load_markerdb(ref)
+        stats_res = sk.composite(None, q)
     assert composite_tsv("q.fq", names, stats) == want and want
+    assert composite_tsv("q.fq", names, stats_res) == want
 
 
 def test_empty_query_is_an_error(sk311, lib_built):

@@ -186,6 +186,7 @@ extern "C" void mk_ctx_destroy(mk_ctx *ctx)
     if (ctx->d_ptab) cudaFree(ctx->d_ptab);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     mk_markerdb_unload(ctx);
+    for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
@@ -283,9 +284,16 @@ extern "C" int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes,
 {
     if (!ctx || !out || (!h_text && nbytes)) return MK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    // the text is uploaded by the stream driver, chunk by chunk under the kernel of the chunk before
     uint8_t *d = nullptr;
-    CKR(upload_text(ctx, h_text, nbytes, &d));
-    return mk_fastq_koc_device(ctx, d, nbytes, out);
+    CKR(mk_scratch(ctx, SB_TEXT, nbytes + 256, &d));
+    CK(cudaMemsetAsync(d + nbytes, 0, 64, ctx->stream));
+    ctx->h_src = (const uint8_t *)h_text;
+    ctx->h_src_all = (const uint8_t *)h_text;
+    int rc = mk_fastq_koc_device(ctx, d, nbytes, out);
+    ctx->h_src = nullptr;
+    ctx->h_src_all = nullptr;
+    return rc;
 }
 
 // popen("<pipecmd or zcat -fc> <path>") like iseq2comem.c:664-669, whole stream into host memory

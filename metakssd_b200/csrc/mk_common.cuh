@@ -87,6 +87,10 @@ struct mk_ctx {
     std::vector<int32_t> comp_lists_flat;
     std::vector<const int32_t *> comp_lists_ptr;
     std::vector<ResidentComponent> mdb;
+    // host text handed from mk_fastq_koc_host to the stream driver (uploaded there, chunk by chunk)
+    const uint8_t *h_src = nullptr;       // pipelined upload (pinned or pageable)
+    const uint8_t *h_src_all = nullptr;   // same pointer; plain upload if the pipelined path is not taken
+    std::vector<cudaEvent_t> chunk_ev;
 };
 
 // Development aid (env MK_TIMING=1): host wall clock between phase marks, with a stream sync at

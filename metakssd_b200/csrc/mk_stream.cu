@@ -25,7 +25,9 @@ struct StreamArgs {
     u64 pos_base;
     u64 line_base;
     u32 tile_bytes;
-    u32 n_tiles;
+    u32 n_tiles;            // tiles [tile_begin, n_tiles) are processed by this launch
+    u32 tile_begin;         // multiple of the ticket group size (k_stream_ws; 0 for a whole-text launch)
+    const u64 *line_base_ptr;   // optional: added to line_base (total of the launch before, chunked host path)
     u64 *tile_desc;
     u32 *tile_counter;
     u32 *count_counter;     // tickets of the count-ahead pass (k_stream_ws)
@@ -857,7 +859,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
     const u32 NBLK = TB / 32;
     const u32 NCHUNK = (TB + 2047u) / 2048u;
     const u32 NMUNIT = (NBLK + 63u) / 64u;
-    const u32 n_groups = (A.n_tiles + WS_G - 1) / WS_G;
+    const u32 gb = A.tile_begin / WS_G;                                  // first group of this launch
+    const u32 n_groups = (A.n_tiles - A.tile_begin + WS_G - 1) / WS_G;   // groups of this launch (tickets are relative)
     auto tile_len = [&](u32 t) -> u32 {
         u64 rem = A.nbytes - (u64)t * TB;
         return rem < TB ? (u32)rem : TB;
@@ -897,6 +900,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         if (lane == 0) {
             u32 ended = 0, j = 0, g = 0, i = 0, cnt = 0;
             u64 P[4] = {0, 0, 0, 0};
+            const u64 LB = A.line_base + (A.line_base_ptr ? *A.line_base_ptr : 0ull);
             bool finished = false;
             for (u32 k = 0;; k++) {
                 const u32 s = k % NS, v = k / NS;
@@ -913,6 +917,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     if (g >= n_groups) finished = true;
                     else {
                         i = 0;
+                        g += gb;
                         const u32 left = A.n_tiles - g * WS_G;
                         cnt = left < (u32)WS_G ? left : (u32)WS_G;
                     }
@@ -926,7 +931,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     if (++ended == WS_NPG) break;
                     continue;
                 }
-                S.Pn[k % (2 * NS)] = A.line_base + P[i & 3u];
+                S.Pn[k % (2 * NS)] = LB + P[i & 3u];
                 i++;
                 stamp(k, 1);
                 const u32 tb = tile_len(t);
@@ -972,7 +977,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     for (int q = 0; q < 8; q++) {
                         const long long idx = i0 + 32 * q + (long long)lane;
                         lo[q] = 0; hi[q] = 1u << 30;
-                        if (idx <= (long long)g) ld_volatile_v2(&A.tile_desc[idx], lo[q], hi[q]);
+                        if (idx <= (long long)g) ld_volatile_v2(&A.tile_desc[gb + idx], lo[q], hi[q]);
                     }
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
@@ -980,7 +985,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                         for (u32 n = 0; (hi[q] >> 30) == 0; n++) {
                             if (n > WD_LIMIT) { watchdog(22, g, (u64)idx, (u64)prev_g, j); good = false; break; }
                             __nanosleep(200);
-                            ld_volatile_v2(&A.tile_desc[idx], lo[q], hi[q]);
+                            ld_volatile_v2(&A.tile_desc[gb + idx], lo[q], hi[q]);
                         }
                         if (idx == (long long)g) { own_lo = lo[q]; own_hi = hi[q]; }
                         else sum += (lo[q] & 0xFFFFu) + (lo[q] >> 16) + (hi[q] & 0xFFFFu) + ((hi[q] >> 16) & 0x3FFFu);
@@ -994,7 +999,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 c4[0] = own_lo & 0xFFFFu; c4[1] = own_lo >> 16; c4[2] = own_hi & 0xFFFFu; c4[3] = (own_hi >> 16) & 0x3FFFu;
                 run_incl = P + c4[0] + c4[1] + c4[2] + c4[3];
                 prev_g = (long long)g;
-                if (lane == 0 && g == n_groups - 1) *A.total_newlines = A.line_base + run_incl;
+                if (lane == 0 && g == n_groups - 1)
+                    *A.total_newlines = A.line_base + (A.line_base_ptr ? *A.line_base_ptr : 0ull) + run_incl;
             }
             if (lane == 0) {
                 S.gq_g[slot] = g;
@@ -1032,7 +1038,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 const u32 c = S.cticket;
                 if (c >= n_groups) break;
                 for (u32 i = cw; i < (u32)WS_G; i += WS_NCW) {
-                    const u32 t = c * WS_G + i;
+                    const u32 t = (gb + c) * WS_G + i;
                     if (t >= A.n_tiles) break;
                     const u32 tb = tile_len(t);
                     const uint8_t *base = A.text + (u64)t * TB;
@@ -1092,7 +1098,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * WS_NCW) : "memory");
                 if (cw == 0 && lane == 0) {
-                    st_volatile_u64(&A.tile_desc[c], (1ull << 62) | ((u64)S.csum[1] << 32) | (u64)S.csum[0]);
+                    st_volatile_u64(&A.tile_desc[gb + c], (1ull << 62) | ((u64)S.csum[1] << 32) | (u64)S.csum[0]);
                     S.csum[0] = 0; S.csum[1] = 0;   // (the team adds to them again only after the next barrier)
                 }
             }
@@ -1522,6 +1528,23 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     size_t smem = ws ? stream_smem_bytes_ws(ctx->bitmap_words * 4, ws_stages(kp)) : stream_smem_bytes(ctx->bitmap_words * 4);
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 
+    // Host source pending (mk_fastq_koc_host): upload and sketch in chunks, the copy of chunk i+1 under
+    // the kernel of chunk i.  Each chunk is one launch over its tile range; the line count carries over
+    // through device memory, candidates accumulate in the same list.
+    const uint8_t *h_src = ctx->h_src;
+    ctx->h_src = nullptr;
+    if (!ws) h_src = nullptr;
+    auto upload_all = [&]() -> int {     // (fallback: plain chunked upload on the compute stream)
+        const size_t CH = (size_t)256 << 20;
+        for (size_t o = 0; o < nbytes; o += CH) {
+            size_t m = nbytes - o < CH ? nbytes - o : CH;
+            CK(cudaMemcpyAsync(const_cast<uint8_t *>(d_text) + o, ctx->h_src_all + o, m, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        return MK_OK;
+    };
+    if (ctx->h_src_all && !h_src) { CKR(upload_all()); }
+    ctx->h_src_all = nullptr;
+
     for (int attempt = 0; attempt < 2; attempt++) {
         u64 *cc, *cp;
         CKR(mk_scratch(ctx, SB_CAND_CODE, (size_t)cap, &cc));
@@ -1530,18 +1553,59 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         CK(cudaMemsetAsync(counters, 0, 128, ctx->stream));
         StreamArgs a;
         a.text = d_text; a.nbytes = nbytes; a.pos_base = pos_base; a.line_base = line_base;
-        a.tile_bytes = tile_bytes; a.n_tiles = n_tiles; a.tile_desc = desc;
+        a.tile_bytes = tile_bytes; a.n_tiles = n_tiles; a.tile_begin = 0; a.line_base_ptr = nullptr; a.tile_desc = desc;
         a.cand_count = counters + 0; a.total_newlines = counters + 1;
         a.tile_counter = (u32 *)(counters + 2); a.flags = (u32 *)(counters + 2) + 1;
         a.count_counter = (u32 *)(counters + 3);
         a.bitmap = ctx->d_bitmap; a.bitmap_bytes = ctx->bitmap_words * 4; a.ptab = ctx->d_ptab; a.two_hash = ctx->kp.mw >= 22 ? 1u : 0u;
         a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp; a.trace = (u64 *)ctx->d_trace; a.wd = counters + 8;
-        u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
+        const u32 threads = ws ? WS_THREADS : MK_STREAM_THREADS;
+        u64 *total_slot = counters + 1;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
-        kern<<<grid, ws ? WS_THREADS : MK_STREAM_THREADS, smem, ctx->stream>>>(a);
+        if (h_src && attempt == 0) {
+            size_t chunk_bytes = (size_t)192 << 20;
+            if (const char *e = getenv("MK_CHUNK_BYTES")) chunk_bytes = (size_t)atoll(e);   // (tests: force many chunks)
+            u32 tiles_per_chunk = (u32)(chunk_bytes / tile_bytes) / WS_G * WS_G;
+            if (tiles_per_chunk < WS_G) tiles_per_chunk = WS_G;
+            const u32 nchunk = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
+            while (ctx->chunk_ev.size() < nchunk) {
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->chunk_ev.push_back(e);
+            }
+            // the copy stream starts after whatever the compute stream still has queued on the buffer
+            CK(cudaEventRecord(ctx->copy_ev[0], ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[0], 0));
+            for (u32 c = 0; c < nchunk; c++) {
+                const u32 t0 = c * tiles_per_chunk, t1 = (c + 1 == nchunk) ? n_tiles : (c + 1) * tiles_per_chunk;
+                const size_t o = (size_t)t0 * tile_bytes;
+                const size_t m = (c + 1 == nchunk) ? nbytes - o : (size_t)(t1 - t0) * tile_bytes;
+                CK(cudaMemcpyAsync(const_cast<uint8_t *>(d_text) + o, h_src + o, m, cudaMemcpyHostToDevice, ctx->copy_stream));
+                CK(cudaEventRecord(ctx->chunk_ev[c], ctx->copy_stream));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->chunk_ev[c], 0));
+                if (c) {
+                    CK(cudaMemsetAsync(a.tile_counter, 0, 4, ctx->stream));
+                    CK(cudaMemsetAsync(a.count_counter, 0, 4, ctx->stream));
+                }
+                a.tile_begin = t0;
+                a.n_tiles = t1;
+                a.line_base_ptr = c ? total_slot : nullptr;                 // total through the chunk before
+                total_slot = counters + ((c & 1u) ? 4 : 1);
+                a.total_newlines = total_slot;
+                const u32 nt = t1 - t0;
+                const u32 grid = nt < (u32)ctx->sm_count ? nt : (u32)ctx->sm_count;
+                kern<<<grid, threads, smem, ctx->stream>>>(a);
+                LAUNCH_COUNT(ctx);
+                CK(cudaGetLastError());
+            }
+            ctx->prof.h2d_bytes += nbytes;
+        } else {
+            u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
+            kern<<<grid, threads, smem, ctx->stream>>>(a);
+            LAUNCH_COUNT(ctx);
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
-        LAUNCH_COUNT(ctx);
-        CK(cudaGetLastError());
         u64 h[16];
         CK(cudaMemcpyAsync(h, counters, 128, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -1575,7 +1639,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
             CK(cudaGetLastError());
         }
         *n_cand = h[0];
-        if (n_newlines) *n_newlines = raw_mode ? line_base : h[1];
+        if (n_newlines) *n_newlines = raw_mode ? line_base : h[total_slot - counters];
         *d_cand_code = cc;
         *d_cand_pos = cp;
         return MK_OK;

@@ -254,3 +254,18 @@ def test_empty_query_is_an_error(sk311, lib_built):
     with pytest.raises(lib_built.MkError) as ei:
         s.composite([ref], [(np.empty(0, np.uint32), np.empty(0, np.uint16))])
     assert ei.value.code == -8
+
+
+def test_host_upload_pipeline_chunks(oracle, sk311, monkeypatch):
+    """mk_fastq_koc_host uploads and sketches chunk by chunk (one launch per chunk, line count and
+    candidates carried over): many small chunks must give the sketch of the whole text."""
+    s, perm, p = sk311
+    S = oracle.synth(77, 12, 200000, 150)
+    text = S.fastq(0, 25000)
+    want = oracle.fastq_koc(p, perm, text)
+    for chunk in ("60000", "1000000", "49152"):
+        monkeypatch.setenv("MK_CHUNK_BYTES", chunk)
+        same_sketch(s.fastq_koc_host(text), want, p)
+    monkeypatch.delenv("MK_CHUNK_BYTES")
+    same_sketch(s.fastq_koc_host(text), want, p)
+

@@ -99,6 +99,15 @@ __device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 byte
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// same, with an L2 evict_first hint: the text is not needed again once it sits in shared memory
+__device__ __forceinline__ void tma_load_1d_last_use(void *dst, const void *src, u32 bytes, u64 *bar)
+{
+    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], pol;\n\t}" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ u64 ld_volatile_u64(const u64 *p)
 {
     u64 v;
@@ -801,8 +810,16 @@ __device__ __forceinline__ void prefetch_l2(const void *p, u32 bytes)
 __device__ __forceinline__ uint4 ld_nc_u128(const void *p)
 {
     uint4 v;
+#ifndef WS_COUNT_NO_HINT
+    // evict_last: the line must still be in L2 when the tile's TMA load arrives a few tile periods later
+    // (without the hint the streaming load is the first to go and DRAM traffic doubles)
+    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_last.b64 pol, 1.0;\n\t"
+                 "ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], pol;\n\t}"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#endif
     return v;
 }
 __device__ __forceinline__ u32 ld_volatile_u32(const u32 *p)
@@ -942,7 +959,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 bytes = (bytes + 15u) & ~15u;
                 fence_proxy_async();
                 mbar_expect_tx(&S.full[s], bytes);
-                tma_load_1d(dst, src, bytes, &S.full[s]);
+                tma_load_1d_last_use(dst, src, bytes, &S.full[s]);
                 if (RAW) {                  // (FASTQ mode: the count-ahead pass has pulled the tile into L2)
                     const u64 pf = (u64)t + (u64)WS_PF_DIST * gridDim.x * WS_G;
                     if (pf < A.n_tiles) {

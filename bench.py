@@ -67,14 +67,55 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: NVML from a thread every few ms
+    (the timed region of the device-resident leg lasts tens of ms), nvidia-smi as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index, self.proc, self.path = index, None, None
+        self.thread, self.stop_flag, self.sm, self.mx, self.reasons = None, False, [], [], set()
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _loop(self, nv, h):
+        R = nv
+        bits = (("hw_slowdown", R.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", R.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", R.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", R.nvmlClocksThrottleReasonSwPowerCap))
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.003)
 
     def start(self):
+        try:
+            import threading
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -85,6 +126,13 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out = {"sm_mhz": statistics.median(self.sm), "sm_max_mhz": max(self.mx),
+                       "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
+            return out
         if not self.proc:
             return out
         self.proc.terminate()
@@ -110,7 +158,7 @@ class ClockSampler:
             pass
         if sm:
             out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
+                   "samples": len(sm), "source": "nvidia-smi"}
         return out
 
 

@@ -46,7 +46,7 @@ __global__ void k_fill_u32(u32 *p, u64 n, u32 v)
 __global__ void __launch_bounds__(256)
 k_acc_insert(const u64 *__restrict__ cand_code, const u64 *__restrict__ cand_pos, const u32 *__restrict__ cand_cnt,
              u64 n, long long keep_below, const u64 *__restrict__ file_off, int n_files, int TL, int code_bits,
-             u64 *__restrict__ keys, u32 *__restrict__ cnt, u64 *__restrict__ minpos, u64 mask)
+             u64 *__restrict__ keys, u32 *__restrict__ cnt, u64 *__restrict__ minpos, u64 mask, u64 *__restrict__ overflow)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -65,9 +65,10 @@ k_acc_insert(const u64 *__restrict__ cand_code, const u64 *__restrict__ cand_pos
     }
     u64 key = (file << code_bits) | cand_code[i];
     u64 h = mix64(key) & mask;
-    for (;;) {
+    for (u32 probes = 0;; probes++) {
         u64 old = atomicCAS((unsigned long long *)&keys[h], EMPTY64, key);
         if (old == EMPTY64 || old == key) break;
+        if (probes > 2048u) { *overflow = 1; return; }   // table sized too small for this input: the host retries
         h = (h + 1) & mask;
     }
     u32 add = cand_cnt ? cand_cnt[i] : 1u;
@@ -120,7 +121,14 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
                       u64 **d_it_pos, u64 *n_items)
 {
     *n_items = 0;
-    u64 cap = pow2_at_least(2 * n + 2);
+    // Reads repeat their k-mers many times over: start with a table a quarter of the candidate count
+    // (clearing and compacting the table is what this step costs) and fall back to 2n slots if a probe
+    // sequence gets long.  Genome batches (file_off) are mostly distinct codes: full size at once.
+    const u64 cap_full = pow2_at_least(2 * n + 2);
+    u64 cap = d_file_off ? cap_full : pow2_at_least(n / 4 + 2);
+    if (cap < (1ull << 16)) cap = cap_full < (1ull << 16) ? cap_full : (1ull << 16);
+    if (cap > cap_full) cap = cap_full;
+  retry:
     u64 *keys, *minpos, *it_key, *it_pos, *counters;
     u32 *cnt, *it_cnt;
     CKR(mk_scratch(ctx, SB_ACC_KEYS, (size_t)cap, &keys));
@@ -133,11 +141,11 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
     CK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(minpos, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(cnt, 0, (size_t)cap * 4, ctx->stream));
-    CK(cudaMemsetAsync(counters + 4, 0, 8, ctx->stream));
+    CK(cudaMemsetAsync(counters + 4, 0, 16, ctx->stream));
     if (n) {
         k_acc_insert<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_code, d_pos, d_cnt, n, keep_below, d_file_off,
                                                                          n_files, ctx->kp.TL, code_bits, keys, cnt,
-                                                                         minpos, cap - 1);
+                                                                         minpos, cap - 1, counters + 5);
         LAUNCH_COUNT(ctx);
     }
     k_acc_compact<<<(unsigned)((cap + 255) / 256), 256, 0, ctx->stream>>>(keys, cnt, minpos, cap, code_bits,
@@ -145,9 +153,15 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
                                                                         counters + 4);
     LAUNCH_COUNT(ctx);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(n_items, counters + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    u64 h2[2];
+    CK(cudaMemcpyAsync(h2, counters + 4, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->prof.d2h_bytes += 8;
+    ctx->prof.d2h_bytes += 16;
+    if (h2[1] && cap < cap_full) {        // a probe sequence ran long: once more with the full-size table
+        cap = cap_full;
+        goto retry;
+    }
+    *n_items = h2[0];
     *d_it_key = it_key;
     *d_it_cnt = it_cnt;
     *d_it_pos = it_pos;

@@ -55,18 +55,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const u32 *__restr
     if (threadIdx.x == 0) bsum[blockIdx.x] = total;
 }
 
-// single block: in-place exclusive scan of m values, writes grand total to *total
+// single block: in-place exclusive scan of m values, writes grand total to *total.
+// Each thread owns SS_IPT consecutive values per sweep (one sweep = 1024 * SS_IPT values).
+#define SS_IPT 8
 __global__ void __launch_bounds__(1024) k_scan_single(u32 *__restrict__ v, u32 m, u64 *__restrict__ total)
 {
     __shared__ u32 ws[33];
     __shared__ u64 carry_s;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
-    u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (u32 base = 0; base < m; base += 1024) {
-        u32 idx = base + threadIdx.x;
-        u32 x = idx < m ? v[idx] : 0;
-        u32 incl = x;
+    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (u32 base = 0; base < m; base += 1024 * SS_IPT) {
+        const u32 i0 = base + threadIdx.x * SS_IPT;
+        u32 x[SS_IPT];
+        u32 sum = 0;
+#pragma unroll
+        for (int j = 0; j < SS_IPT; j++) {
+            x[j] = i0 + j < m ? v[i0 + j] : 0;
+            sum += x[j];
+        }
+        u32 incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             u32 t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -86,8 +94,13 @@ __global__ void __launch_bounds__(1024) k_scan_single(u32 *__restrict__ v, u32 m
             if (lane == 31) ws[32] = si;
         }
         __syncthreads();
-        u64 carry = carry_s;
-        if (idx < m) v[idx] = (u32)(carry + ws[wid] + incl - x);
+        const u64 carry = carry_s;
+        u32 off = (u32)(carry + ws[wid] + incl - sum);
+#pragma unroll
+        for (int j = 0; j < SS_IPT; j++) {
+            if (i0 + j < m) v[i0 + j] = off;
+            off += x[j];
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + ws[32];
         __syncthreads();

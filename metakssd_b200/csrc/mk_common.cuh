@@ -91,6 +91,7 @@ struct mk_ctx {
     const uint8_t *h_src = nullptr;       // pipelined upload (pinned or pageable)
     const uint8_t *h_src_all = nullptr;   // same pointer; plain upload if the pipelined path is not taken
     std::vector<cudaEvent_t> chunk_ev;
+    u64 h_maxpos = 0;                     // read-back slot of mk_runs_finalize_device
 };
 
 // Development aid (env MK_TIMING=1): host wall clock between phase marks, with a stream sync at

@@ -125,7 +125,7 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
     // (clearing and compacting the table is what this step costs) and fall back to 2n slots if a probe
     // sequence gets long.  Genome batches (file_off) are mostly distinct codes: full size at once.
     const u64 cap_full = pow2_at_least(2 * n + 2);
-    u64 cap = d_file_off ? cap_full : pow2_at_least(n / 4 + 2);
+    u64 cap = (d_file_off || d_cnt) ? cap_full : pow2_at_least(n / 4 + 2);   // (runs being merged are mostly distinct too)
     if (cap < (1ull << 16)) cap = cap_full < (1ull << 16) ? cap_full : (1ull << 16);
     if (cap > cap_full) cap = cap_full;
   retry:
@@ -516,6 +516,19 @@ extern "C" int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const u
     return runs_sorted_by_code(ctx, it_key, it_cnt, it_pos, n_items, merged);
 }
 
+// largest value of an array (bounds the radix passes of the first-position sort)
+__global__ void __launch_bounds__(256) k_max_u64(const u64 *__restrict__ v, u64 n, u64 *__restrict__ out)
+{
+    u64 m = 0;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x) m = v[i] > m ? v[i] : m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 x = __shfl_xor_sync(0xffffffffu, m, o);
+        m = x > m ? x : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned long long *)out, (unsigned long long)m);
+}
+
 extern "C" int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
                                        const uint32_t *d_count, uint64_t n, mk_sketch *out)
 {
@@ -525,9 +538,23 @@ extern "C" int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, cons
     u64 *it_key, *it_pos, n_items;
     u32 *it_cnt;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    if (n) {   // (queued before accumulate's own read-back, which also synchronises this one)
+        u64 *d_max;
+        CKR(mk_scratch(ctx, SB_MISC, 64, &d_max));
+        CK(cudaMemsetAsync(d_max + 4, 0, 8, ctx->stream));
+        k_max_u64<<<ctx->sm_count, 256, 0, ctx->stream>>>((const u64 *)d_firstpos, n, d_max + 4);
+        LAUNCH_COUNT(ctx);
+        CK(cudaMemcpyAsync(&ctx->h_maxpos, d_max + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CKR(accumulate(ctx, (const u64 *)d_code, (const u64 *)d_firstpos, d_count, n, LLONG_MAX, nullptr, 1,
                    ctx->info.code_bits, false, &it_key, &it_cnt, &it_pos, &n_items));
+    if (n) {
+        int b = 1;
+        while (b < 64 && (ctx->h_maxpos >> b)) b++;
+        ctx->pos_bits = b;
+    }
     int rc = mk_order_and_emit(ctx, it_key, it_cnt, it_pos, n_items, 1, true, false, out);
+    ctx->pos_bits = 64;
     cudaEventRecord(ctx->ev3, ctx->stream);
     cudaEventSynchronize(ctx->ev3);
     float ms = 0;

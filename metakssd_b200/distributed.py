@@ -43,7 +43,8 @@ def split_sizes_by_code_range(codes: torch.Tensor, world: int, code_bits: int) -
 
 
 def all_to_all_runs(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tensor, send_sizes: list, group=None):
-    """Variable-size all-to-all of three parallel arrays; returns the received (code, pos, cnt)."""
+    """Variable-size all-to-all of three parallel arrays; returns the received (code, pos, cnt).
+    The three arrays travel as one (n, 3) int64 buffer: two collectives per exchange (sizes, payload)."""
     world = dist.get_world_size(group)
     dev = code.device
     send = torch.tensor(send_sizes, dtype=torch.int64, device=dev)
@@ -51,13 +52,10 @@ def all_to_all_runs(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tensor, se
     dist.all_to_all_single(recv, send, group=group)
     recv_sizes = recv.tolist()
     n = int(sum(recv_sizes))
-    out = []
-    for t in (code, pos, cnt):
-        o = torch.empty(n, dtype=t.dtype, device=dev)
-        dist.all_to_all_single(o, t.contiguous(), output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
-                               group=group)
-        out.append(o)
-    return out[0], out[1], out[2]
+    payload = torch.stack((code, pos, cnt.to(torch.int64)), dim=1).contiguous()
+    out = torch.empty((n, 3), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(out, payload, output_split_sizes=recv_sizes, input_split_sizes=send_sizes, group=group)
+    return out[:, 0].contiguous(), out[:, 1].contiguous(), out[:, 2].to(cnt.dtype)
 
 
 def merge_runs_reference(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tensor):
@@ -78,17 +76,30 @@ def merge_runs_reference(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tenso
 def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_last: bool, group=None):
     """The whole multi-GPU step for this rank's shard.  Returns the final Sketch on rank 0 (None
     elsewhere).  `sk` is this rank's Sketcher; d_text its shard in device memory."""
+    import os, time
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", sk.info.device)
+    _t = [time.perf_counter()] if os.environ.get("MK_TIMING") else None
+
+    def _mark(what):
+        if _t is not None:
+            torch.cuda.synchronize(dev)
+            now = time.perf_counter()
+            print("[mk timing r%d] %-18s %7.3f ms" % (rank, what, (now - _t[0]) * 1e3), flush=True)
+            _t[0] = now
     runs = sk.fastq_partial_device(d_text, nbytes, pos_base, line_base, is_last)
+    _mark("partial")
     n = int(runs.n)
     code = device_tensor(runs.d_code, n, torch.int64, dev)
     pos = device_tensor(runs.d_firstpos, n, torch.int64, dev)
     cnt = device_tensor(runs.d_count, n, torch.int32, dev)
     sizes = split_sizes_by_code_range(code, world, sk.info.code_bits)
+    _mark("split sizes")
     rc, rp, rk = all_to_all_runs(code, pos, cnt, sizes, group)
     torch.cuda.current_stream(dev).synchronize()
+    _mark("all_to_all")
     merged = sk.runs_merge_device(rc, rp, rk, int(rc.numel()))
+    _mark("merge")
     m = int(merged.n)
     mc = device_tensor(merged.d_code, m, torch.int64, dev)
     mp = device_tensor(merged.d_firstpos, m, torch.int64, dev)
@@ -96,6 +107,9 @@ def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_la
     to_root = [m] + [0] * (world - 1)
     gc, gp, gk = all_to_all_runs(mc, mp, mk, to_root, group)
     torch.cuda.current_stream(dev).synchronize()
+    _mark("gather to root")
     if rank != 0:
         return None
-    return sk.runs_finalize_device(gc, gp, gk, int(gc.numel()))
+    out = sk.runs_finalize_device(gc, gp, gk, int(gc.numel()))
+    _mark("finalize")
+    return out

@@ -270,10 +270,9 @@ def run_ours(args):
         def step_host():
             if world == 1:
                 return composite(sk.fastq_koc_host(h_text), False)
-            # multi-GPU: the shard goes through the same host-buffer upload, then the sharded path
-            d_text[:e_nbytes].copy_(h_text, non_blocking=True)
-            torch.cuda.current_stream(dev).synchronize()
-            s = D.sketch_sharded(sk, d_text, e_nbytes, pos_base, 0, rank == world - 1)
+            # multi-GPU: every rank uploads its shard from its own pinned buffer (chunks overlapped with
+            # the kernel), then the sharded path
+            s = D.sketch_sharded(sk, h_text, e_nbytes, pos_base, 0, rank == world - 1, host_text=True)
             return composite(s, False) if rank == 0 else None
 
         e_steps = max(2, min(args.steps, 3))

@@ -171,6 +171,10 @@ typedef struct mk_runs {
 } mk_runs;
 int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,
                             int is_last, mk_runs *runs);
+/* Same with the shard in HOST memory (pinned for full speed): uploaded and sketched chunk by chunk like
+ * mk_fastq_koc_host, into a library-owned device buffer. */
+int mk_fastq_partial_host(mk_ctx *ctx, const void *h_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,
+                          int is_last, mk_runs *runs);
 /* Merge runs (possibly from several ranks, concatenated in device memory, any order): sum the
  * counts per code with saturation at 65535, keep the minimum firstpos, then reproduce the
  * reference's hash-slot order and split by component. */

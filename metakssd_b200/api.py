@@ -85,7 +85,7 @@ EXPORTS = [
     "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
     "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
-    "mk_composite_component_resident", "mk_fastq_partial_device",
+    "mk_composite_component_resident", "mk_fastq_partial_device", "mk_fastq_partial_host",
     "mk_runs_finalize_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
@@ -133,6 +133,7 @@ def load():
     L.mk_composite_component_resident.argtypes = [vp, i32, vp, vp, u64, u64]
     L.mk_composite_hits.argtypes = [vp, C.POINTER(C.POINTER(C.POINTER(C.c_int32)))]
     L.mk_fastq_partial_device.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
+    L.mk_fastq_partial_host.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
     L.mk_runs_finalize_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkSketch)]
     L.mk_runs_merge_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkRuns)]
     L.mk_count_newlines_device.argtypes = [vp, vp, sz, C.POINTER(u64)]
@@ -395,6 +396,12 @@ class Sketcher:
         r = MkRuns()
         self._ck(self._L.mk_fastq_partial_device(self._h, _ptr(d_text), nbytes, pos_base, line_base,
                                                  1 if is_last else 0, C.byref(r)))
+        return r
+
+    def fastq_partial_host(self, h_text, nbytes: int, pos_base: int, line_base: int, is_last: bool) -> MkRuns:
+        r = MkRuns()
+        self._ck(self._L.mk_fastq_partial_host(self._h, _ptr(h_text), nbytes, pos_base, line_base,
+                                               1 if is_last else 0, C.byref(r)))
         return r
 
     def runs_finalize_device(self, d_code, d_pos, d_cnt, n: int) -> Sketch:

@@ -504,6 +504,22 @@ extern "C" int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t n
     return rc;
 }
 
+extern "C" int mk_fastq_partial_host(mk_ctx *ctx, const void *h_text, size_t nbytes, uint64_t pos_base,
+                                     uint64_t line_base, int is_last, mk_runs *runs)
+{
+    if (!ctx || !runs || (!h_text && nbytes)) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    CKR(mk_scratch(ctx, SB_TEXT, nbytes + 256, &d));
+    CK(cudaMemsetAsync(d + nbytes, 0, 64, ctx->stream));
+    ctx->h_src = (const uint8_t *)h_text;      // consumed by the stream driver (pipelined upload)
+    ctx->h_src_all = (const uint8_t *)h_text;
+    int rc = mk_fastq_partial_device(ctx, d, nbytes, pos_base, line_base, is_last, runs);
+    ctx->h_src = nullptr;
+    ctx->h_src_all = nullptr;
+    return rc;
+}
+
 extern "C" int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
                                     const uint32_t *d_count, uint64_t n, mk_runs *merged)
 {

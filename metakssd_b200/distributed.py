@@ -73,9 +73,11 @@ def merge_runs_reference(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tenso
     return uniq, pmin, torch.clamp(ksum, max=65535).to(cnt.dtype)
 
 
-def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_last: bool, group=None):
+def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_last: bool, group=None,
+                   host_text: bool = False):
     """The whole multi-GPU step for this rank's shard.  Returns the final Sketch on rank 0 (None
-    elsewhere).  `sk` is this rank's Sketcher; d_text its shard in device memory."""
+    elsewhere).  `sk` is this rank's Sketcher; d_text its shard in device memory (or, with
+    host_text=True, in host memory: uploaded chunk by chunk under the kernel)."""
     import os, time
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     dev = torch.device("cuda", sk.info.device)
@@ -87,7 +89,7 @@ def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_la
             now = time.perf_counter()
             print("[mk timing r%d] %-18s %7.3f ms" % (rank, what, (now - _t[0]) * 1e3), flush=True)
             _t[0] = now
-    runs = sk.fastq_partial_device(d_text, nbytes, pos_base, line_base, is_last)
+    runs = (sk.fastq_partial_host if host_text else sk.fastq_partial_device)(d_text, nbytes, pos_base, line_base, is_last)
     _mark("partial")
     n = int(runs.n)
     code = device_tensor(runs.d_code, n, torch.int64, dev)

@@ -31,6 +31,12 @@ WORKER = textwrap.dedent('''
     d = torch.empty(nb + 256, dtype=torch.uint8, device=dev)
     sk.synth_fastq_device(spec.P, spec.cdf32, spec.species, r0, r1, d, d.numel())
     got = D.sketch_sharded(sk, d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1)
+    # the same shard from pinned host memory, uploaded in (forced small) chunks under the kernel
+    h = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+    h.copy_(d[:nb]); torch.cuda.synchronize(dev)
+    os.environ["MK_CHUNK_BYTES"] = "3000000"
+    got_h = D.sketch_sharded(sk, h, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, host_text=True)
+    del os.environ["MK_CHUNK_BYTES"]
     if rank == 0:
         nball = spec.fastq_bytes(0, world * per)
         full = torch.empty(nball + 256, dtype=torch.uint8, device=dev)
@@ -40,6 +46,8 @@ WORKER = textwrap.dedent('''
         for c in range(len(want.codes)):
             assert np.array_equal(got.codes[c], want.codes[c]), "codes/order differ"
             assert np.array_equal(got.counts[c], want.counts[c]), "counts differ"
+            assert np.array_equal(got_h.codes[c], want.codes[c]), "host-text path: codes/order differ"
+            assert np.array_equal(got_h.counts[c], want.counts[c]), "host-text path: counts differ"
         print("MULTI_OK", want.n_total)
     dist.barrier()
     dist.destroy_process_group()

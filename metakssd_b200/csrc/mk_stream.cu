@@ -48,6 +48,7 @@ struct StreamArgs {
 
 #define TBUF_STRIDE (MK_HALO + MK_MAX_TILE + 96) // keeps the stage buffers 128-byte aligned
 #define FLAG_LONG_LINE 2u
+#define FLAG_MAYBE_LONG 8u   // some 2 KB chunk holds no newline: the host runs the exact line-length check
 #define FLAG_WATCHDOG 4u     // a wait inside k_stream gave up (diagnostics in StreamArgs::wd)
 #define WD_LIMIT (1u << 21)
 
@@ -1109,7 +1110,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     u32 total = acc_lo + acc_hi;
                     total = (total & 0xFFFFu) + (total >> 16);
                     total = __reduce_add_sync(0xffffffffu, total);
-                    if (lane == 0 && total == 0 && tb == TB && TB >= 4096) atomicOr(A.flags, FLAG_LONG_LINE);
                     // descriptor = four 14-bit per-tile counts at bit 16 i (a tile has < 2^14 bytes)
                     if (lane == 0 && total) atomicAdd(&S.csum[i >> 1], total << (16u * (i & 1u)));
                 }
@@ -1190,6 +1190,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     if (lane >= (u32)o) incl += x;
                 }
                 if (lane < NCHUNK) G.cpre[lane] = incl - v;
+                // a line of 4095+ bytes (fgets splits it, MK_ERR_LONG_LINE) covers a whole chunk
+                const u32 cend = (lane + 1u) * 2048u < TB ? (lane + 1u) * 2048u : TB;
+                if (__any_sync(0xffffffffu, lane < NCHUNK && v == 0 && cend <= tb) && lane == 0)
+                    atomicOr(A.flags, FLAG_MAYBE_LONG);
             }
             if (old == WS_SCT - 1 && lane == 0) S.scnt[s] = 0;
             __syncwarp();
@@ -1456,6 +1460,49 @@ extern "C" int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t 
     return MK_OK;
 }
 
+// ---- exact line-length check (only when the stream kernel saw a newline-free chunk) ------------
+// fgets(buf, 4096) splits a line once 4095 bytes came without a newline; what the reference does with
+// the pieces depends on stale buffer contents, so such input is refused.  A run of >= 4095 newline-free
+// bytes covers an aligned 2 KB chunk entirely: one warp per such chunk measures the run around it.
+__global__ void __launch_bounds__(256) k_long_line_check(const uint8_t *__restrict__ text, u64 n, u32 *__restrict__ flag)
+{
+    const u32 lane = threadIdx.x & 31;
+    const u64 nchunks = n / 2048;
+    const u64 warp0 = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 c = warp0; c < nchunks; c += nwarps) {
+        const uint4 *q = reinterpret_cast<const uint4 *>(text + c * 2048 + (u64)lane * 64);
+        u32 any = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint4 v = q[j];
+            u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                u32 t7 = ((w[i] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                any |= ~(t7 | w[i]) & 0x80808080u;
+            }
+        }
+        if (__any_sync(0xffffffffu, any != 0)) continue;
+        const u64 lo = c * 2048, hi = lo + 2048;
+        u64 back = 0, fwd = 0;                       // newline-free bytes right before lo / right after hi
+        while (back < 2048 && back < lo) {
+            const u64 d = back + lane;               // looks at byte lo - 1 - d
+            const bool nl = d < lo && text[lo - 1 - d] == '\n';
+            const u32 m = __ballot_sync(0xffffffffu, nl);
+            if (m) { back += __ffs(m) - 1; break; }
+            back = back + 32 < lo ? back + 32 : lo;
+        }
+        while (back + 2048 + fwd < 4095 && hi + fwd < n) {
+            const u64 p = hi + fwd + lane;
+            const bool nl = p < n && text[p] == '\n';
+            const u32 m = __ballot_sync(0xffffffffu, nl);
+            if (m) { fwd += __ffs(m) - 1; break; }
+            fwd = hi + fwd + 32 < n ? fwd + 32 : n - hi;
+        }
+        if (back + 2048 + fwd >= 4095 && lane == 0) atomicOr(flag, 1u);
+    }
+}
+
 // ---- host driver -------------------------------------------------------------------------------
 typedef void (*stream_kernel_t)(const StreamArgs);
 
@@ -1642,8 +1689,18 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
                      (unsigned long long)((h[15] >> 21) & 0x1FFFFF), (unsigned long long)(h[15] & 0x1FFFFF), n_tiles);
             return MK_ERR_CUDA;
         }
-        if (!raw_mode && (flags & FLAG_LONG_LINE)) {
-            snprintf(ctx->err, sizeof(ctx->err), "FASTQ line longer than 4095 bytes");
+        bool long_line = !raw_mode && (flags & FLAG_LONG_LINE);
+        if (!raw_mode && !long_line && (flags & FLAG_MAYBE_LONG)) {     // rare: measure the line exactly
+            u32 *d_flag = (u32 *)(counters + 6), h_flag = 0;
+            CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
+            k_long_line_check<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_text, (u64)nbytes, d_flag);
+            LAUNCH_COUNT(ctx);
+            CK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            long_line = h_flag != 0;
+        }
+        if (long_line) {
+            snprintf(ctx->err, sizeof(ctx->err), "FASTQ line of 4095 bytes or more (fgets(…, 4096) would split it)");
             return MK_ERR_LONG_LINE;
         }
         if (h[0] > cap) { // candidate buffer too small: size it exactly and run again

@@ -269,3 +269,29 @@ def test_host_upload_pipeline_chunks(oracle, sk311, monkeypatch):
     monkeypatch.delenv("MK_CHUNK_BYTES")
     same_sketch(s.fastq_koc_host(text), want, p)
 
+
+def test_long_lines_exact_threshold(oracle, sk311):
+    """fgets(buf, 4096) splits a line once 4095 bytes came without a newline: such input is refused
+    (MK_ERR_LONG_LINE) exactly from that length on, wherever the line sits; shorter lines are sketched."""
+    import metakssd_b200 as M
+    s, perm, p = sk311
+    S = oracle.synth(91, 6, 100000, 150)
+    genome = bytes(S.fasta(0)).split(b"\n", 1)[1].replace(b"\n", b"")
+    recs = bytes(S.fastq(0, 3000))
+
+    def with_line(seq_len, where):
+        seq = genome[:seq_len]
+        rec = b"@long\n" + seq + b"\n+\n" + b"I" * seq_len + b"\n"
+        cut = recs.find(b"\n@r", where) + 1
+        return recs[:cut] + rec + recs[cut:]
+
+    for seq_len, where in ((3000, 100), (4094, 50000), (4094, 400000)):
+        text = with_line(seq_len, where)
+        want = oracle.fastq_koc(p, perm, np.frombuffer(text, np.uint8))
+        same_sketch(s.fastq_koc_host(np.frombuffer(text, np.uint8).copy()), want, p)
+    for seq_len, where in ((4095, 100), (4095, 300000), (5000, 200000), (13000, 7), (40000, 123456)):
+        text = with_line(seq_len, where)
+        with pytest.raises(M.MkError) as e:
+            s.fastq_koc_host(np.frombuffer(text, np.uint8).copy())
+        assert e.value.code == -6, (seq_len, where, e.value)   # MK_ERR_LONG_LINE
+

@@ -714,25 +714,28 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 }
 
 // ================================================================================================
-// k_stream_ws — warp-specialised, barrier-free variant of the same pipeline.
+// k_stream_ws — warp-specialised, barrier-free variant of the same pipeline (the default).
 //
 // The unit-pulling kernel above spends a large share of its issue slots on shared-memory atomics,
 // fetch loops and one block barrier per tile.  Here every warp has a fixed role and a plain loop;
-// tiles flow through a ring of WS_NS shared-memory stages and the roles hand a stage over with
-// mbarriers (arrive / try_wait.parity), never with __syncthreads:
+// tiles flow through a ring of NS shared-memory stages and the roles hand a stage over with
+// mbarriers (arrive / try_wait.parity), never with __syncthreads.  A multi-warp role waits through
+// its leader warp (the others park on a named barrier).  Tickets are groups of WS_G consecutive tiles.
 //
-//   loader   (1 lane)   waits until the probe warps released the stage, claims the next ticket,
-//                       starts its TMA                                           -> full[s]
-//   front    (NFW warps) scan their chunks of the tile for '\n'                    -> scanned[s]
-//                       then build the sequence-byte masks + item list of the tile
-//                       before (software pipelined, so that the resolver has a whole
-//                       scan phase to finish)                                       -> ready[s]
-//   resolver (1 warp)   publishes the tile's newline count, sums the counts published since
-//                       this CTA's previous tile (decoupled look-back)             -> resolved[s]
-//   probe    (NPW warps) probe a static, per-tile rotated share of the items        -> done[s]
+//   loader      (1 lane)    waits until the probe group released the stage, takes the next tile of
+//                           its group, starts the TMA                              -> full[s]
+//   resolver    (1 warp)    claims the CTA's next group ticket and sums the newline counts published
+//                           for the tickets since its previous group             -> mailbox gready[]
+//   count-ahead (WS_NCW)    a team that counts the newlines of whole groups straight from global
+//                           memory, WS_WINDOW x gridDim groups ahead of the load front, and publishes
+//                           one packed descriptor per group (read by every CTA's resolver)
+//   scan        (2 teams)   newline mask + in-tile prefix of newline counts per 32-byte block
+//                                                                                  -> scanned[s]
+//   mask        (2 teams)   sequence-byte mask per block, item list of the tile   -> ready[s]
+//   probe       (2 groups)  probe a static, per-tile rotated share of the items   -> done[s]
 //
-// The k-th tile of a CTA always uses stage k % WS_NS, so every role derives stage and mbarrier
-// parity from its own loop counter.
+// Teams / groups take alternating tiles (k % 2).  The k-th tile of a CTA always uses stage k % NS, so
+// every role derives stage and mbarrier parity from its own loop counter.
 // ================================================================================================
 #ifndef WS_NS
 #define WS_NS 6        // ring stages
@@ -775,9 +778,6 @@ static_assert(WS_G == 4 && WS_TILE < 16384, "descriptor packing");
 #endif
 #define WS_TBUF (MK_HALO + WS_TILE + 96)
 
-#ifndef WS_HITBUF
-#define WS_HITBUF 94     // hits buffered per tile (~14 expected at L3K11); the rest goes straight to global memory
-#endif
 struct WsStage {
     u32 nlm[WS_BLK];             // newline mask of each block; the mask warps overwrite it in place with
                                  // the block's sequence-byte mask (same index, same thread)
@@ -785,8 +785,6 @@ struct WsStage {
     uint16_t items[WS_BLK];
     u32 ctot[WS_CHUNK];
     u32 cpre[WS_CHUNK];
-    u32 nhit, pfin, pcur;        // hits of this tile so far, rounds completed, next round of items
-    uint16_t hit[WS_HITBUF];     // tile offsets of the hits (flushed with one global atomic per tile)
 };
 template <int NS>
 struct WsSmem {
@@ -860,12 +858,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             mbar_init(&S.full[s], 1);
             mbar_init(&S.scanned[s], WS_SCT);
             mbar_init(&S.ready[s], WS_MKT);
-#ifdef WS_PROBE_DYNAMIC
-            mbar_init(&S.done[s], WS_NPG * WS_NPW);
-#else
             mbar_init(&S.done[s], WS_NPW);
-#endif
-            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0; S.tot[s] = 0; S.st[s].nhit = 0; S.st[s].pfin = 0; S.st[s].pcur = 0;
+            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0; S.tot[s] = 0;
         }
         for (int q = 0; q < 2; q++) { mbar_init(&S.gready[q], 1); mbar_init(&S.gfree[q], 1); }
         S.cticket = 0; S.csum[0] = 0; S.csum[1] = 0; S.abort = 0;
@@ -942,7 +936,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 }
                 const u32 t = finished ? 0xFFFFFFFFu : g * WS_G + i;
                 S.n_items[s] = 0;
-                S.st[s].pcur = 0; S.st[s].pfin = 0; S.st[s].nhit = 0;
                 S.tile[s] = t;
                 if (t >= A.n_tiles) {       // end marker: one per probe group, in consecutive ring slots
                     mbar_arrive(&S.full[s]);
@@ -1268,67 +1261,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             }
         }
     } else {
-#ifdef WS_PROBE_DYNAMIC
-        // ======================= probe ==========================================================
-        // Every probe warp visits every tile and pulls rounds of 32 items from it; a warp that finds a
-        // tile exhausted moves on to the next one, so the warps spread over the tiles in flight.
-        for (u32 k = 0;; k++) {
-            const u32 s = k % NS, par = (k / NS) & 1u;
-            stamp(k, 0);
-            if (!wait_on(&S.ready[s], par, 40, k)) break;
-            stamp(k, 1);
-            const u32 t = S.tile[s];
-            if (t >= A.n_tiles) break;
-            WsStage &G = S.st[s];
-            const uint8_t *tx = tbuf + s * WS_TBUF;
-            const u64 T = (u64)t * TB;
-            const u32 n = S.n_items[s];
-            const u32 rounds = (n + 31u) >> 5;
-            // (visiting a tile that has no round left costs two shared-memory loads and the arrive)
-            // (lane 0's view, broadcast: lanes reading the cursor at different times would split the warp)
-            while (__shfl_sync(0xffffffffu, *(volatile u32 *)&G.pcur, 0) < rounds) {
-                u32 r = 0;
-                if (lane == 0) r = atomicAdd(&G.pcur, 1u);
-                r = __shfl_sync(0xffffffffu, r, 0);
-                if (r >= rounds) break;
-                const u32 it = r * 32u + lane;
-                if (it < n) {
-                    const u32 b = G.items[it];
-                    u32 Aw[4];
-                    u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
-                    hits &= G.nlm[b];                       // sequence-byte mask by now
-                    while (hits) {
-                        u32 j = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
-                        const u32 h = atomicAdd(&G.nhit, 1u);
-                        if (h < WS_HITBUF) G.hit[h] = (uint16_t)(32 * b + j);
-                        else emit_hit(A, T + 32 * b + j);
-                    }
-                }
-                __syncwarp();
-                // the warp that completes the tile's last round appends the buffered hits to the global list
-                u32 fin = 0;
-                if (lane == 0) { __threadfence_block(); fin = atomicAdd(&G.pfin, 1u); }
-                fin = __shfl_sync(0xffffffffu, fin, 0);
-                if (fin == rounds - 1) {
-                    __threadfence_block();
-                    const u32 nh = G.nhit < WS_HITBUF ? G.nhit : (u32)WS_HITBUF;
-                    if (nh) {
-                        u64 base = 0;
-                        if (lane == 0) base = atomicAdd((unsigned long long *)A.cand_count, (unsigned long long)nh);
-                        base = __shfl_sync(0xffffffffu, base, 0);
-                        for (u32 i = lane; i < nh; i += 32)
-                            if (base + i < A.cand_cap) A.cand_pos[base + i] = T + G.hit[i];
-                    }
-                    __syncwarp();
-                }
-            }
-            stamp(k, 2);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.done[s]);   // (the loader resets the tile's cursors when it refills the stage)
-        }
-#else
         // ======================= probe ==========================================================
         const u32 pg = (wid - WS_ROLE0 - WS_NFW) / WS_NPW, pw = (wid - WS_ROLE0 - WS_NFW) % WS_NPW;
         for (u32 k = pg;; k += WS_NPG) {
@@ -1361,7 +1293,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.done[s]);
         }
-#endif
     }
 }
 

@@ -346,12 +346,16 @@ extern "C" int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_
     size_t nbytes = (size_t)offsets[n_files];
     uint8_t *dense = nullptr;
     u64 dense_bytes = 0, *d_dense_off = nullptr;
+    MkPhaseClock pc(ctx->stream);
     CKR(mk_fasta_compact(ctx, (const uint8_t *)d_text, nbytes, (const u64 *)offsets, n_files, &dense, &dense_bytes,
                          &d_dense_off));
     u64 *cc = nullptr, *cp = nullptr, n_cand = 0;
+    pc.mark("fasta compact");
     CKR(mk_stream_fastq(ctx, dense, (size_t)dense_bytes, 0, 0, true, &cc, &cp, &n_cand, nullptr));
+    pc.mark("stream+verify");
     ctx->pos_bits = bits_for(dense_bytes);
     int rc = mk_finalize_candidates(ctx, cc, cp, n_cand, LLONG_MAX, d_dense_off, n_files, false, out);
+    pc.mark("finalize");
     ctx->pos_bits = 64;
     if (rc != MK_OK)
         for (int f = 0; f < n_files; f++) mk_sketch_free(&out[f]);

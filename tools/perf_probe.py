@@ -5,7 +5,7 @@ import numpy as np, torch
 import metakssd_b200 as M
 import oracle as O
 
-k, subk, L = 11, 6, 3
+k, subk, L = [int(x) for x in os.environ.get("KSL", "11,6,3").split(",")]
 nreads = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
 sid, perm = O.make_shuf(1234, k, subk, L)
 S = O.synth(42, 100, 1_000_000, 150)

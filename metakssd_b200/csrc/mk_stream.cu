@@ -836,6 +836,13 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// cold path, kept out of line so that the roles' loops stay compact in the instruction cache
+__device__ __noinline__ void ws_watchdog_report(u32 *flags, u64 *wd, u32 site, u32 wid, u64 a, u64 b, u64 c, u64 d, u64 tiles)
+{
+    if (atomicOr(flags, FLAG_WATCHDOG) & FLAG_WATCHDOG) return;   // first report wins
+    wd[0] = site; wd[1] = blockIdx.x; wd[2] = wid; wd[3] = a; wd[4] = b; wd[5] = c; wd[6] = d; wd[7] = tiles;
+}
+
 template <int ROTOFF, u32 WORDMASK, int PREW, bool RAW, int NS>
 __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_constant__ StreamArgs A)
 {
@@ -878,12 +885,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         return rem < TB ? (u32)rem : TB;
     };
     auto watchdog = [&](u32 site, u64 a, u64 b, u64 c, u64 d) {
-        if (atomicOr(A.flags, FLAG_WATCHDOG) & FLAG_WATCHDOG) return;
-        A.wd[0] = site; A.wd[1] = blockIdx.x; A.wd[2] = wid; A.wd[3] = a; A.wd[4] = b; A.wd[5] = c; A.wd[6] = d;
-        A.wd[7] = ((u64)S.tile[0] << 42) | ((u64)S.tile[1] << 21) | (u64)S.tile[2];
+        ws_watchdog_report(A.flags, A.wd, site, wid, a, b, c, d,
+                           ((u64)S.tile[0] << 42) | ((u64)S.tile[1] << 21) | (u64)S.tile[2]);
     };
-    auto stamp = [&](u32 k, u32 slot) {      // development aid: clock64() stamps of CTA 0, first 48 tiles
+    auto stamp = [&](u32 k, u32 slot) {      // development aid (build with -DMK_TRACE): clock64() stamps of CTA 0
+#ifdef MK_TRACE
         if (A.trace && blockIdx.x == 0 && k < 48 && lane == 0) A.trace[((u64)k * 32 + wid) * 4 + slot] = clock64();
+#else
+        (void)k; (void)slot;
+#endif
     };
     // wait with a watchdog; false = gave up (the role then leaves the kernel)
     auto wait_on = [&](u64 *bar, u32 parity, u32 site, u32 k) -> bool {

@@ -1,4 +1,5 @@
-"""Role timeline of CTA 0 for the warp-specialised kernel (development tool)."""
+"""Role timeline of CTA 0 for the warp-specialised kernel (development tool).
+Needs a library built with the stamps compiled in: MK_NVCC_FLAGS=-DMK_TRACE python -m metakssd_b200.build --force"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, ctypes as C

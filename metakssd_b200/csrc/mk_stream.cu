@@ -1205,7 +1205,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         auto mask = [&](u32 s, u32 t, u32 k) {
             WsStage &G = S.st[s];
             const u32 tb = tile_len(t);
-            const u32 P = RAW ? 0u : (u32)S.Pn[k % (2 * NS)];
+            const u32 P = RAW ? 0u : (u32)S.Pn[k];      // k = tile sequence number mod 2 NS
             for (u32 u = member; u < NMUNIT; u += WS_MKT) {
                 u32 pm[2];
 #pragma unroll
@@ -1244,18 +1244,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             if (lane == 0) { __threadfence_block(); mbar_arrive(&S.ready[s]); }
         };
         if (is_scan) {
-            for (u32 k = team;; k += WS_NPG) {
-                const u32 s = k % NS, par = (k / NS) & 1u;
+            // (stage, parity and the 2 NS-periodic index follow k incrementally: no divisions in the loops)
+            for (u32 k = team, s = team % NS, par = (team / NS) & 1u, k2 = team % (2 * NS);; k += WS_NPG) {
+                if (k != team) {
+                    s += WS_NPG; if (s >= NS) { s -= NS; par ^= 1u; }
+                    k2 += WS_NPG; if (k2 >= 2 * NS) k2 -= 2 * NS;
+                }
                 if (!role_wait(&S.full[s], nullptr, par, 30, k, 4 + team, WS_SCT, member == 0)) break;
                 const u32 t = S.tile[s];
                 if (t >= A.n_tiles) break;                  // (one end marker per team)
                 stamp(k, 0);
-                scan(s, t, k);
+                scan(s, t, k2);
                 stamp(k, 1);
             }
         } else {
-            for (u32 k = team;; k += WS_NPG) {
-                const u32 s = k % NS, par = (k / NS) & 1u;
+            for (u32 k = team, s = team % NS, par = (team / NS) & 1u, k2 = team % (2 * NS);; k += WS_NPG) {
+                if (k != team) {
+                    s += WS_NPG; if (s >= NS) { s -= NS; par ^= 1u; }
+                    k2 += WS_NPG; if (k2 >= 2 * NS) k2 -= 2 * NS;
+                }
                 // (an end marker's `scanned` never completes: look at the tile id first)
                 if (!role_wait(&S.full[s], nullptr, par, 32, k, 4 + WS_NPG + team, WS_MKT, member == 0)) break;
                 const u32 t = S.tile[s];
@@ -1266,15 +1273,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 }
                 if (!role_wait(&S.scanned[s], nullptr, par, 33, k, 4 + WS_NPG + team, WS_MKT, member == 0)) break;
                 stamp(k, 2);
-                mask(s, t, k);
+                mask(s, t, k2);
                 stamp(k, 3);
             }
         }
     } else {
         // ======================= probe ==========================================================
         const u32 pg = (wid - WS_ROLE0 - WS_NFW) / WS_NPW, pw = (wid - WS_ROLE0 - WS_NFW) % WS_NPW;
-        for (u32 k = pg;; k += WS_NPG) {
-            const u32 s = k % NS, par = (k / NS) & 1u;
+        for (u32 k = pg, s = pg % NS, par = (pg / NS) & 1u, rot = 0;; k += WS_NPG) {
+            if (k != pg) {
+                s += WS_NPG; if (s >= NS) { s -= NS; par ^= 1u; }
+                if (++rot == WS_NPW) rot = 0;          // rot = (k / WS_NPG) % WS_NPW
+            }
             stamp(k, 0);
             if (!role_wait(&S.ready[s], nullptr, par, 40, k, 2 + pg, WS_NPW, pw == 0)) break;
             stamp(k, 1);
@@ -1284,7 +1294,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             const uint8_t *tx = tbuf + s * WS_TBUF;
             const u64 T = (u64)t * TB;
             const u32 n = S.n_items[s];
-            for (u32 r = (pw + WS_NPW - ((k / WS_NPG) % WS_NPW)) % WS_NPW; r * 32u < n; r += WS_NPW) {
+            for (u32 r = pw >= rot ? pw - rot : pw + WS_NPW - rot; r * 32u < n; r += WS_NPW) {
                 const u32 it = r * 32u + lane;
                 if (it < n) {
                     const u32 b = G.items[it];

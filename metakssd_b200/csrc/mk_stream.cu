@@ -1000,14 +1000,21 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                         lo[q] = 0; hi[q] = 1u << 30;
                         if (idx <= (long long)g) ld_volatile_v2(&A.tile_desc[gb + idx], lo[q], hi[q]);
                     }
+                    // (descriptors are published well ahead: the retry path is cold and kept out of the unrolled code)
+                    u32 ready = hi[0] & hi[1] & hi[2] & hi[3] & hi[4] & hi[5] & hi[6] & hi[7];
+                    for (u32 n = 0; __any_sync(0xffffffffu, (ready >> 30) == 0); n++) {
+                        if (n > WD_LIMIT) { if (lane == 0) watchdog(22, g, (u64)i0, (u64)prev_g, j); good = false; break; }
+                        __nanosleep(200);
+#pragma unroll 1
+                        for (int q = 0; q < 8; q++) {
+                            const long long idx = i0 + 32 * q + (long long)lane;
+                            if (idx <= (long long)g && (hi[q] >> 30) == 0) ld_volatile_v2(&A.tile_desc[gb + idx], lo[q], hi[q]);
+                        }
+                        ready = hi[0] & hi[1] & hi[2] & hi[3] & hi[4] & hi[5] & hi[6] & hi[7];
+                    }
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
                         const long long idx = i0 + 32 * q + (long long)lane;
-                        for (u32 n = 0; (hi[q] >> 30) == 0; n++) {
-                            if (n > WD_LIMIT) { watchdog(22, g, (u64)idx, (u64)prev_g, j); good = false; break; }
-                            __nanosleep(200);
-                            ld_volatile_v2(&A.tile_desc[gb + idx], lo[q], hi[q]);
-                        }
                         if (idx == (long long)g) { own_lo = lo[q]; own_hi = hi[q]; }
                         else sum += (lo[q] & 0xFFFFu) + (lo[q] >> 16) + (hi[q] & 0xFFFFu) + ((hi[q] >> 16) & 0x3FFFu);
                     }
@@ -1094,6 +1101,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                         }
                     } else {
                         const u32 nvec = (tb + 15u) >> 4;
+#pragma unroll 1
                         for (u32 v = lane; v < nvec; v += 32u) {
                             uint4 q = ld_nc_u128(base + 16u * v);
                             u32 w[4] = {q.x, q.y, q.z, q.w};
@@ -1138,8 +1146,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             for (u32 c = member; c < NCHUNK; c += WS_SCT) {
                 const u32 off = c * 2048u + lane * 64u;        // my 64 bytes (two blocks)
                 if (t == 0 && c == 0 && lane < MK_HALO / 4) reinterpret_cast<u32 *>(tx)[lane] = 0;
-                if (off + 64u > tb && off < TB) {               // blank what lies outside the text
+                if (off + 64u > tb && off < TB) {               // blank what lies outside the text (last tile only)
                     u32 from = off > tb ? off : tb;
+#pragma unroll 1
                     for (u32 i = from; i < off + 64u; i++) tx[MK_HALO + i] = 0;
                 }
                 if (RAW) continue;

@@ -278,6 +278,9 @@ __device__ __forceinline__ void load_block(const uint8_t *blk, int shift_s, u32 
 {
     u32 W[PREW + 3];
     const uint4 *q = reinterpret_cast<const uint4 *>(blk - 16 * PREW);
+#ifdef MK_ROTATED_BLOCK_LOADS
+    // lanes alternate the order of their 16-byte pieces so that neighbouring blocks never hit the same
+    // banks in the same wavefront (measured: no gain over the plain order, kept for reference)
     const bool rot = (threadIdx.x >> 2) & 1;
     if (PREW == 1) {
         u32 w0 = pack16(q[rot ? 1 : 0]), w1 = pack16(q[rot ? 2 : 1]), w2 = pack16(q[rot ? 0 : 2]);
@@ -286,6 +289,10 @@ __device__ __forceinline__ void load_block(const uint8_t *blk, int shift_s, u32 
         u32 w0 = pack16(q[rot ? 2 : 0]), w1 = pack16(q[rot ? 3 : 1]), w2 = pack16(q[rot ? 0 : 2]), w3 = pack16(q[rot ? 1 : 3]);
         W[0] = rot ? w2 : w0; W[1] = rot ? w3 : w1; W[2] = rot ? w0 : w2; W[PREW + 1] = rot ? w1 : w3;
     }
+#else
+#pragma unroll
+    for (int i = 0; i < PREW + 2; i++) W[i] = pack16(q[i]);
+#endif
     W[PREW + 2] = 0;
     A[0] = __funnelshift_r(W[0], W[1], shift_s);
     A[1] = __funnelshift_r(W[1], W[2], shift_s);
@@ -1155,7 +1162,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 u32 m0 = 0, m1 = 0;
                 if (off < TB) {
                     const uint4 *q = reinterpret_cast<const uint4 *>(tx + MK_HALO + off);
-                    const u32 rot = (lane >> 1) & 3u;           // conflict-free piece order (see k_stream)
+                    const u32 rot = (lane >> 1) & 3u;           // conflict-free piece order (plain order: -1 %)
 #pragma unroll
                     for (int k4 = 0; k4 < 4; k4++) {
                         const u32 pc = (k4 + rot) & 3u;

@@ -180,6 +180,10 @@ int mk_fastq_partial_host(mk_ctx *ctx, const void *h_text, size_t nbytes, uint64
  * reference's hash-slot order and split by component. */
 int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos, const uint32_t *d_count,
                             uint64_t n, mk_sketch *out);
+/* Same for runs whose codes are already distinct (the concatenation of code ranges merged by their
+ * owners): skips the accumulation.  Undefined result if a code occurs twice. */
+int mk_runs_finalize_distinct_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
+                                     const uint32_t *d_count, uint64_t n, mk_sketch *out);
 /* Merge only (no ordering): device-resident reduced runs sorted by code. */
 int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos, const uint32_t *d_count,
                          uint64_t n, mk_runs *merged);

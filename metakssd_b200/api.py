@@ -86,7 +86,7 @@ EXPORTS = [
     "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
     "mk_composite_component_resident", "mk_fastq_partial_device", "mk_fastq_partial_host",
-    "mk_runs_finalize_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
+    "mk_runs_finalize_device", "mk_runs_finalize_distinct_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
 ]
@@ -135,6 +135,7 @@ def load():
     L.mk_fastq_partial_device.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
     L.mk_fastq_partial_host.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
     L.mk_runs_finalize_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkSketch)]
+    L.mk_runs_finalize_distinct_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkSketch)]
     L.mk_runs_merge_device.argtypes = [vp, vp, vp, vp, u64, C.POINTER(MkRuns)]
     L.mk_count_newlines_device.argtypes = [vp, vp, sz, C.POINTER(u64)]
     L.mk_synth_fastq_device.argtypes = [vp, C.POINTER(MksParams), vp, vp, u64, u64, vp, sz, C.POINTER(sz)]
@@ -404,9 +405,10 @@ class Sketcher:
                                                1 if is_last else 0, C.byref(r)))
         return r
 
-    def runs_finalize_device(self, d_code, d_pos, d_cnt, n: int) -> Sketch:
+    def runs_finalize_device(self, d_code, d_pos, d_cnt, n: int, distinct: bool = False) -> Sketch:
         sk = MkSketch()
-        self._ck(self._L.mk_runs_finalize_device(self._h, _ptr(d_code), _ptr(d_pos), _ptr(d_cnt), n, C.byref(sk)))
+        fn = self._L.mk_runs_finalize_distinct_device if distinct else self._L.mk_runs_finalize_device
+        self._ck(fn(self._h, _ptr(d_code), _ptr(d_pos), _ptr(d_cnt), n, C.byref(sk)))
         return _take_sketch(sk, True)
 
     def runs_merge_device(self, d_code, d_pos, d_cnt, n: int) -> MkRuns:

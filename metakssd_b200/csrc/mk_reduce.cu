@@ -545,8 +545,31 @@ __global__ void __launch_bounds__(256) k_max_u64(const u64 *__restrict__ v, u64 
     if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned long long *)out, (unsigned long long)m);
 }
 
+__global__ void __launch_bounds__(256)
+k_widen_runs(const u64 *__restrict__ code, const u64 *__restrict__ pos, const u32 *__restrict__ cnt, u64 n,
+             u64 *__restrict__ it_key, u32 *__restrict__ it_cnt, u64 *__restrict__ it_pos)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { it_key[i] = code[i]; it_cnt[i] = cnt[i]; it_pos[i] = pos[i]; }
+}
+
+static int runs_finalize(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos, const uint32_t *d_count,
+                         uint64_t n, bool distinct, mk_sketch *out);
+
 extern "C" int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
                                        const uint32_t *d_count, uint64_t n, mk_sketch *out)
+{
+    return runs_finalize(ctx, d_code, d_firstpos, d_count, n, false, out);
+}
+
+extern "C" int mk_runs_finalize_distinct_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos,
+                                                const uint32_t *d_count, uint64_t n, mk_sketch *out)
+{
+    return runs_finalize(ctx, d_code, d_firstpos, d_count, n, true, out);
+}
+
+static int runs_finalize(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_firstpos, const uint32_t *d_count,
+                         uint64_t n, bool distinct, mk_sketch *out)
 {
     if (!ctx || !out) return MK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -562,8 +585,19 @@ extern "C" int mk_runs_finalize_device(mk_ctx *ctx, const uint64_t *d_code, cons
         LAUNCH_COUNT(ctx);
         CK(cudaMemcpyAsync(&ctx->h_maxpos, d_max + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    CKR(accumulate(ctx, (const u64 *)d_code, (const u64 *)d_firstpos, d_count, n, LLONG_MAX, nullptr, 1,
-                   ctx->info.code_bits, false, &it_key, &it_cnt, &it_pos, &n_items));
+    if (distinct && n) {      // every code occurs once (ranges merged by their owners): nothing to accumulate
+        CKR(mk_scratch(ctx, SB_IT_CODE, (size_t)n + 1, &it_key));
+        CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n + 1, &it_cnt));
+        CKR(mk_scratch(ctx, SB_IT_POS, (size_t)n + 1, &it_pos));
+        k_widen_runs<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const u64 *)d_code, (const u64 *)d_firstpos,
+                                                                         d_count, n, it_key, it_cnt, it_pos);
+        LAUNCH_COUNT(ctx);
+        CK(cudaStreamSynchronize(ctx->stream));       // (h_maxpos has arrived)
+        n_items = n;
+    } else {
+        CKR(accumulate(ctx, (const u64 *)d_code, (const u64 *)d_firstpos, d_count, n, LLONG_MAX, nullptr, 1,
+                       ctx->info.code_bits, false, &it_key, &it_cnt, &it_pos, &n_items));
+    }
     if (n) {
         int b = 1;
         while (b < 64 && (ctx->h_maxpos >> b)) b++;

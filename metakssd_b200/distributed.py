@@ -112,6 +112,6 @@ def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_la
     _mark("gather to root")
     if rank != 0:
         return None
-    out = sk.runs_finalize_device(gc, gp, gk, int(gc.numel()))
+    out = sk.runs_finalize_device(gc, gp, gk, int(gc.numel()), distinct=True)   # owners' ranges are disjoint
     _mark("finalize")
     return out

@@ -210,10 +210,15 @@ def run_ours(args):
     if rank == 0:
         sk.load_markerdb(mdb.comp)
 
+    names_c = M.SpeciesNames(mdb.names)
+
     def composite(sketch, resident):
-        qry = [(sketch.codes[c], sketch.counts[c]) for c in range(len(sketch.codes))]
-        stats = sk.composite(None if resident else mdb.comp, qry)
-        return M.composite_tsv("reads.fq", mdb.names, stats)
+        if resident:        # MarkerDB and the sketch just produced are both on the device
+            stats = sk.composite_last()
+        else:
+            qry = [(sketch.codes[c], sketch.counts[c]) for c in range(len(sketch.codes))]
+            stats = sk.composite(mdb.comp, qry)
+        return M.coverage_tsv("reads.fq", names_c, stats)
 
     def step_device():
         if world == 1:

@@ -142,6 +142,9 @@ int mk_markerdb_load(mk_ctx *ctx, int component, const uint32_t *ref_codes, cons
 int mk_markerdb_unload(mk_ctx *ctx);
 int mk_composite_component_resident(mk_ctx *ctx, int component, const uint32_t *qry_codes,
                                     const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi);
+/* mk_composite_component_resident() with the query taken from the device: component `component` of the
+ * -A sketch this context produced last (mk_fastq_koc_* or mk_runs_finalize_*): nothing is uploaded. */
+int mk_composite_component_last(mk_ctx *ctx, int component);
 /* Per-species order statistics over the accumulated hits, the integers the reference prints
  * (command_composite.c:598-624); the two float ratios are sum/n and lastsum/lastn. */
 typedef struct mk_species_stat {
@@ -153,6 +156,11 @@ typedef struct mk_species_stat {
     int32_t max;        /* a[n]                                                             */
 } mk_species_stat;
 int mk_composite_stats(mk_ctx *ctx, mk_species_stat *stats /* [n_species] */);
+/* The species_coverage lines exactly as command_composite.c:582-624 prints them (host code, no device
+ * work): species by matched k-mers descending, ties in index order, stop below 6 matches.  Returns the
+ * text length (excluding the NUL); at most cap bytes are written, call with buf = NULL to size it. */
+size_t mk_format_species_coverage(const char *qry_name, const char *const *ref_names, const mk_species_stat *stats,
+                                  int n_species, char *buf, size_t cap);
 /* Raw hit lists in reference layout: lists[s][0] = n, lists[s][1..n] = counts in MarkerDB code
  * order (component-major).  Library-owned until the next mk_composite_begin/destroy. */
 int mk_composite_hits(mk_ctx *ctx, const int32_t *const **lists);

@@ -85,7 +85,8 @@ EXPORTS = [
     "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
     "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
-    "mk_composite_component_resident", "mk_fastq_partial_device", "mk_fastq_partial_host",
+    "mk_composite_component_resident", "mk_composite_component_last", "mk_format_species_coverage",
+    "mk_fastq_partial_device", "mk_fastq_partial_host",
     "mk_runs_finalize_device", "mk_runs_finalize_distinct_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
@@ -131,6 +132,9 @@ def load():
     L.mk_markerdb_load.argtypes = [vp, i32, vp, vp, i32]
     L.mk_markerdb_unload.argtypes = [vp]
     L.mk_composite_component_resident.argtypes = [vp, i32, vp, vp, u64, u64]
+    L.mk_composite_component_last.argtypes = [vp, i32]
+    L.mk_format_species_coverage.argtypes = [C.c_char_p, vp, vp, i32, vp, sz]
+    L.mk_format_species_coverage.restype = sz
     L.mk_composite_hits.argtypes = [vp, C.POINTER(C.POINTER(C.POINTER(C.c_int32)))]
     L.mk_fastq_partial_device.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
     L.mk_fastq_partial_host.argtypes = [vp, vp, sz, u64, u64, i32, C.POINTER(MkRuns)]
@@ -357,6 +361,17 @@ class Sketcher:
             ri = np.ascontiguousarray(ri, dtype=np.uint64)
             self._ck(self._L.mk_markerdb_load(self._h, c, rc.ctypes.data, ri.ctypes.data, self._mdb_species))
 
+    def composite_last(self):
+        """Resident MarkerDB (load_markerdb) against the -A sketch this context produced last, which is
+        still on the device: no upload at all.  Returns the per-species stats array."""
+        S = self._mdb_species
+        self._ck(self._L.mk_composite_begin(self._h, S))
+        for c in range(self._mdb_components):
+            self._ck(self._L.mk_composite_component_last(self._h, c))
+        stats = np.zeros(S, dtype=STATS_DTYPE)
+        self._ck(self._L.mk_composite_stats(self._h, stats.ctypes.data))
+        return stats
+
     def composite(self, ref_comp, qry_comp, want_lists: bool = False):
         """ref_comp: per component (codes uint32[], index uint64[S+1]); qry_comp: per component
         (codes uint32[], counts uint16[]) of ONE query.  Returns the per-species stats array
@@ -379,8 +394,7 @@ class Sketcher:
             qa = np.ascontiguousarray(qa, dtype=np.uint16)
             self._ck(self._L.mk_composite_component(self._h, rc.ctypes.data, ri.ctypes.data, S, qc.ctypes.data,
                                                     qa.ctypes.data, 0, qc.size))
-        stats = np.zeros(S, dtype=np.dtype([("n", "<i4"), ("sum", "<i4"), ("lastsum", "<i4"), ("lastn", "<i4"),
-                                            ("median", "<i4"), ("max", "<i4")]))
+        stats = np.zeros(S, dtype=STATS_DTYPE)
         self._ck(self._L.mk_composite_stats(self._h, stats.ctypes.data))
         if not want_lists:
             return stats
@@ -479,6 +493,30 @@ def read_sketch_dir(path: str):
     hdr = dict(shuf_id=shuf_id, koc=bool(koc), kmerlen=kmerlen, dim_rd_len=dim_rd_len, comp_num=comp_num,
                infile_num=infile_num, all_ctx_ct=all_ctx)
     return hdr, names, combco, index, abund
+
+
+STATS_DTYPE = np.dtype([("n", "<i4"), ("sum", "<i4"), ("lastsum", "<i4"), ("lastn", "<i4"), ("median", "<i4"),
+                        ("max", "<i4")])
+
+
+class SpeciesNames:
+    """Species names prepared once for mk_format_species_coverage (a C array of C strings)."""
+
+    def __init__(self, names):
+        self.names = list(names)
+        self._enc = [n.encode() for n in self.names]
+        self.carr = (C.c_char_p * len(self._enc))(*self._enc)
+
+
+def coverage_tsv(qry_name: str, names: SpeciesNames, stats) -> str:
+    """species_coverage lines through the library's C formatter (same text as composite_tsv)."""
+    L = load()
+    stats = np.ascontiguousarray(stats, dtype=STATS_DTYPE)
+    q = qry_name.encode()
+    need = L.mk_format_species_coverage(q, names.carr, stats.ctypes.data, len(names.names), None, 0)
+    buf = C.create_string_buffer(need + 1)
+    L.mk_format_species_coverage(q, names.carr, stats.ctypes.data, len(names.names), buf, need + 1)
+    return buf.raw[:need].decode()
 
 
 def composite_tsv(qry_name: str, ref_names, stats) -> str:

@@ -8,6 +8,7 @@
 // in MarkerDB order (component-major) into a per-context store.  Statistics: one radix sort of
 // (species << 16 | count) and one thread per species.
 #include "mk_common.cuh"
+#include <algorithm>
 
 #define EMPTY64 0xFFFFFFFFFFFFFFFFull
 
@@ -82,7 +83,8 @@ extern "C" int mk_composite_begin(mk_ctx *ctx, int n_species)
 // host arrays of the call (uploaded now) or a component made resident by mk_markerdb_load().
 static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, const u32 *res_ref,
                                const u64 *res_index, u64 r, int n_species, const uint32_t *qry_codes,
-                               const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi)
+                               const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi,
+                               const u32 *dev_qry = nullptr, const uint16_t *dev_qcnt = nullptr)
 {
     CK(cudaSetDevice(ctx->device));
     const u64 q = qry_hi - qry_lo;
@@ -141,9 +143,14 @@ static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uin
         CK(cudaMemcpyAsync(d_index, ref_index, (size_t)(n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
         ctx->prof.h2d_bytes += r * 4 + (u64)(n_species + 1) * 8;
     }
-    CK(cudaMemcpyAsync(d_qry, qry_codes + qry_lo, (size_t)q * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_qcnt, qry_counts + qry_lo, (size_t)q * 2, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->prof.h2d_bytes += q * 6;
+    if (dev_qry) {                      // the query is the sketch this context has just produced: already on the device
+        d_qry = const_cast<u32 *>(dev_qry) + qry_lo;
+        d_qcnt = const_cast<uint16_t *>(dev_qcnt) + qry_lo;
+    } else {
+        CK(cudaMemcpyAsync(d_qry, qry_codes + qry_lo, (size_t)q * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d_qcnt, qry_counts + qry_lo, (size_t)q * 2, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->prof.h2d_bytes += q * 6;
+    }
     CK(cudaMemsetAsync(d_keys, 0xFF, (size_t)cap * 8, ctx->stream));
     CK(cudaMemsetAsync(d_idx, 0xFF, (size_t)cap * 4, ctx->stream));
     k_cq_insert<<<(unsigned)((q + 255) / 256), 256, 0, ctx->stream>>>(d_qry, q, d_keys, d_idx, (u32)(cap - 1));
@@ -217,6 +224,47 @@ extern "C" int mk_composite_component_resident(mk_ctx *ctx, int component, const
     if (!m.d_index || m.n_species != ctx->comp_species) return MK_ERR_ARG;
     return composite_component(ctx, nullptr, nullptr, m.d_ref, m.d_index, m.r, m.n_species, qry_codes, qry_counts, qry_lo,
                                qry_hi);
+}
+
+extern "C" int mk_composite_component_last(mk_ctx *ctx, int component)
+{
+    if (!ctx || component < 0 || (size_t)component >= ctx->mdb.size()) return MK_ERR_ARG;
+    const ResidentComponent &m = ctx->mdb[(size_t)component];
+    if (!m.d_index || m.n_species != ctx->comp_species) return MK_ERR_ARG;
+    if (!ctx->last_out_code || (size_t)component + 1 >= ctx->last_seg.size()) {
+        snprintf(ctx->err, sizeof(ctx->err), "no -A sketch of this context is resident (or it has fewer components)");
+        return MK_ERR_ARG;
+    }
+    return composite_component(ctx, nullptr, nullptr, m.d_ref, m.d_index, m.r, m.n_species, nullptr, nullptr,
+                               ctx->last_seg[(size_t)component], ctx->last_seg[(size_t)component + 1], ctx->last_out_code,
+                               ctx->last_out_cnt);
+}
+
+// ---- species_coverage lines (host): command_composite.c:582-624 ------------------------------------
+// Species ordered by matched k-mers, descending (glibc's qsort is a stable merge sort: ties stay in
+// index order), stopping at the first with fewer than 6; the two ratios are float divisions printed
+// with %f.  Returns the number of bytes the text needs (excluding the NUL); writes at most cap bytes.
+extern "C" size_t mk_format_species_coverage(const char *qry_name, const char *const *ref_names,
+                                             const mk_species_stat *stats, int n_species, char *buf, size_t cap)
+{
+    if (!qry_name || !ref_names || !stats || n_species < 0) return 0;
+    std::vector<int> order((size_t)n_species);
+    for (int i = 0; i < n_species; i++) order[(size_t)i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return stats[a].n > stats[b].n; });
+    size_t need = 0;
+    char line[1024];
+    for (int i = 0; i < n_species; i++) {
+        const mk_species_stat *s = &stats[order[(size_t)i]];
+        if (s->n < 6) break;
+        int m = snprintf(line, sizeof(line), "%s\t%s\t%d\t%f\t%f\t%d\t%d\n", qry_name, ref_names[order[(size_t)i]], s->n,
+                         (float)s->sum / s->n, (float)s->lastsum / s->lastn, s->median, s->max);
+        if (m < 0) continue;
+        if ((size_t)m >= sizeof(line)) m = (int)sizeof(line) - 1;
+        if (buf && need + (size_t)m < cap) memcpy(buf + need, line, (size_t)m);
+        need += (size_t)m;
+    }
+    if (buf && cap) buf[need < cap ? need : cap - 1] = 0;
+    return need;
 }
 
 __global__ void __launch_bounds__(256)

@@ -292,6 +292,8 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
         s->counts = with_counts ? (uint16_t **)calloc((size_t)cn, sizeof(uint16_t *)) : nullptr;
         if (!s->n || !s->codes || (with_counts && !s->counts)) return MK_ERR_NOMEM;
     }
+    ctx->last_out_code = nullptr;
+    ctx->last_out_cnt = nullptr;
     if (n == 0) return MK_OK;
     if (n >= 0xFFFFFFF0ull) return MK_ERR_UNSUPPORTED;
     const u64 nb = (n + 255) / 256;
@@ -393,6 +395,14 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
     h_seg[nseg] = n;
     for (long long s = (long long)nseg - 1; s >= 0; s--)
         if (h_seg[s] == EMPTY64) h_seg[s] = h_seg[s + 1];
+    // a single-file -A sketch stays usable on the device (mk_composite_component_last)
+    ctx->last_out_code = nullptr;
+    ctx->last_out_cnt = nullptr;
+    if (n_files == 1 && with_counts) {
+        ctx->last_out_code = out_code;
+        ctx->last_out_cnt = out_cnt;
+        ctx->last_seg.assign(h_seg, h_seg + nseg + 1);
+    }
     for (int f = 0; f < n_files; f++) {
         mk_sketch *s = &out[f];
         for (int c = 0; c < cn; c++) {

@@ -226,6 +226,11 @@ def test_composite_matches_oracle(oracle, sk311):
     s.load_markerdb([(ref_codes, ref_index)])
     for _ in range(2):
         assert composite_tsv("reads.fq", names, s.composite(None, [(g.codes[0], g.counts[0])])) == want
+    # ... and with the query taken from the device: the sketch this context produced last
+    from metakssd_b200 import SpeciesNames, coverage_tsv
+    g2 = s.fastq_koc_host(S.fastq(0, 60000))
+    assert np.array_equal(g2.codes[0], g.codes[0])
+    assert coverage_tsv("reads.fq", SpeciesNames(names), s.composite_last()) == want
 
 
 def test_composite_multi_component(oracle, lib_built, shuf):

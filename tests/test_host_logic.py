@@ -110,3 +110,26 @@ def test_markerdb_semantics(lib_built):
     allc = np.concatenate([s.codes[0] for s in sk])
     u, n = np.unique(allc, return_counts=True)
     assert set(codes.tolist()) == set(u[n == 1].tolist())
+
+
+def test_c_coverage_formatter_matches_python(lib_built):
+    """mk_format_species_coverage (host C, command_composite.c:582-624) against the Python statement of
+    the same rule: order by matches descending with ties in index order, cut below 6, float32 ratios."""
+    from metakssd_b200 import SpeciesNames, composite_tsv, coverage_tsv
+    from metakssd_b200.api import STATS_DTYPE
+    rng = np.random.default_rng(5)
+    S = 400
+    st = np.zeros(S, dtype=STATS_DTYPE)
+    st["n"] = rng.choice([0, 3, 5, 6, 6, 7, 50, 50, 1000, 123456], size=S)
+    st["sum"] = rng.integers(1, 2 ** 31 - 1, size=S)
+    st["sum"][::7] = -5                      # int wrap-around of the reference's `int sum`
+    st["lastsum"] = rng.integers(0, 70000, size=S)
+    st["lastn"] = np.maximum(1, st["n"] // 100 + 1)
+    st["median"] = rng.integers(0, 65536, size=S)
+    st["max"] = rng.integers(0, 65536, size=S)
+    names = ["%d_species_%d" % (i + 1, i) for i in range(S)]
+    want = composite_tsv("some/query.fq", names, st)
+    got = coverage_tsv("some/query.fq", SpeciesNames(names), st)
+    assert got == want and want.count("\n") > 100
+    assert coverage_tsv("q", SpeciesNames(names), np.zeros(S, dtype=STATS_DTYPE)) == ""
+

@@ -56,56 +56,59 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const u32 *__restr
 }
 
 // single block: in-place exclusive scan of m values, writes grand total to *total.
-// Each thread owns SS_IPT consecutive values per sweep (one sweep = 1024 * SS_IPT values).
-#define SS_IPT 8
+// Every thread owns one contiguous run of 4 * R4 values (read as 16-byte vectors, v must be 16-byte
+// aligned): one pass to sum the run, one block-wide scan of the 1024 sums, one pass to write the
+// prefixes — two memory round trips whatever m is (the old sweep-by-sweep version cost one per 8 K values).
 __global__ void __launch_bounds__(1024) k_scan_single(u32 *__restrict__ v, u32 m, u64 *__restrict__ total)
 {
     __shared__ u32 ws[33];
-    __shared__ u64 carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (u32 base = 0; base < m; base += 1024 * SS_IPT) {
-        const u32 i0 = base + threadIdx.x * SS_IPT;
-        u32 x[SS_IPT];
-        u32 sum = 0;
-#pragma unroll
-        for (int j = 0; j < SS_IPT; j++) {
-            x[j] = i0 + j < m ? v[i0 + j] : 0;
-            sum += x[j];
+    const u32 R4 = (m + 4095u) / 4096u;                  // vectors per thread
+    const u32 base = threadIdx.x * 4u * R4;
+    u32 sum = 0;
+    for (u32 j = 0; j < R4; j++) {
+        const u32 i = base + 4u * j;
+        if (i + 3u < m) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(v + i);
+            sum += q.x + q.y + q.z + q.w;
+        } else {
+            for (u32 e = i; e < m && e < i + 4u; e++) sum += v[e];
         }
-        u32 incl = sum;
+    }
+    u32 incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (u32)o) incl += t;
+    }
+    if (lane == 31) ws[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        u32 s = ws[lane];
+        u32 si = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            u32 t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= (u32)o) incl += t;
+            u32 t = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= (u32)o) si += t;
         }
-        if (lane == 31) ws[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-            u32 s = ws[lane];
-            u32 si = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                u32 t = __shfl_up_sync(0xffffffffu, si, o);
-                if (lane >= (u32)o) si += t;
-            }
-            ws[lane] = si - s;
-            if (lane == 31) ws[32] = si;
-        }
-        __syncthreads();
-        const u64 carry = carry_s;
-        u32 off = (u32)(carry + ws[wid] + incl - sum);
-#pragma unroll
-        for (int j = 0; j < SS_IPT; j++) {
-            if (i0 + j < m) v[i0 + j] = off;
-            off += x[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + ws[32];
-        __syncthreads();
+        ws[lane] = si - s;
+        if (lane == 31) ws[32] = si;
     }
-    if (threadIdx.x == 0 && total) *total = carry_s;
+    __syncthreads();
+    u32 off = ws[wid] + incl - sum;
+    for (u32 j = 0; j < R4; j++) {
+        const u32 i = base + 4u * j;
+        if (i + 3u < m) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(v + i);
+            uint4 o4;
+            o4.x = off; o4.y = off + q.x; o4.z = o4.y + q.y; o4.w = o4.z + q.z;
+            off = o4.w + q.w;
+            *reinterpret_cast<uint4 *>(v + i) = o4;
+        } else {
+            for (u32 e = i; e < m && e < i + 4u; e++) { const u32 x = v[e]; v[e] = off; off += x; }
+        }
+    }
+    if (threadIdx.x == 0 && total) *total = ws[32];
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)

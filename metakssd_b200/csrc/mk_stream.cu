@@ -803,7 +803,7 @@ struct WsSmem {
     u32 cticket, csum[2];        // count team: current group ticket, its packed per-tile newline counts so far
     u32 abort;                   // a leader's wait gave up: the whole role leaves
     u64 Pn[2 * NS];           // newlines before the k-th tile of this CTA (index k % (2 NS))
-    u32 tile[NS], n_items[NS], scnt[NS], tot[NS];
+    u32 tile[NS], n_items[NS], scnt[NS];
 };
 
 __device__ __forceinline__ void prefetch_l2(const void *p, u32 bytes)
@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             mbar_init(&S.scanned[s], WS_SCT);
             mbar_init(&S.ready[s], WS_MKT);
             mbar_init(&S.done[s], WS_NPW);
-            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0; S.tot[s] = 0;
+            S.n_items[s] = 0; S.tile[s] = 0xFFFFFFFFu; S.scnt[s] = 0;
         }
         for (int q = 0; q < 2; q++) { mbar_init(&S.gready[q], 1); mbar_init(&S.gfree[q], 1); }
         S.cticket = 0; S.csum[0] = 0; S.csum[1] = 0; S.abort = 0;
@@ -1194,8 +1194,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             }
             fence_proxy_async();
             __syncwarp();
-            // The front warp that finishes the tile's scan publishes its newline count right away:
-            // other CTAs' look-backs depend on it and must never wait behind our own look-back.
+            // The warp of the team that finishes the tile's scan last turns the per-chunk counts into the
+            // in-tile prefix the mask stage needs (the counts other CTAs look back on come from the
+            // count-ahead pass, not from here).
             u32 old = 0;
             if (lane == 0) { __threadfence_block(); old = atomicAdd(&S.scnt[s], 1u); }
             old = __shfl_sync(0xffffffffu, old, 0);

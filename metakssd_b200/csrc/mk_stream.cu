@@ -856,6 +856,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
     extern __shared__ __align__(128) uint8_t smem[];
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31, wid = tid >> 5;
+    // byte-compare constants kept in registers, so that (w ^ c) & m is ONE three-input LOP3 (with immediates
+    // the compiler needs two instructions per word)
+    // (derived from a launch parameter in a way no compiler pass can fold: tile_bytes < 2^31)
+    const u32 c0a = 0x0A0A0A0Au + (A.tile_bytes >> 31), c7f = 0x7F7F7F7Fu + (A.tile_bytes >> 31);
     const u32 bm_bytes = (A.bitmap_bytes + 127u) & ~127u;
     u32 *bm = reinterpret_cast<u32 *>(smem);
     uint8_t *tbuf = smem + bm_bytes;
@@ -1098,7 +1102,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                                 u32 w[4] = {q[jj].x, q[jj].y, q[jj].z, q[jj].w};
 #pragma unroll
                                 for (int x = 0; x < 4; x++) {
-                                    u32 t7 = ((w[x] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                                    u32 t7 = ((w[x] ^ c0a) & c7f) + c7f;
                                     u32 f = ~(t7 | w[x]) & 0x80808080u;     // 0x80 where the byte is a newline
                                     acc = __umulhi(f, 1u << 25) + acc;      // += f >> 7 (<= 4 * WS_CNT_BATCH per byte lane)
                                 }
@@ -1171,7 +1175,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                         u32 m = 0;
 #pragma unroll
                         for (int j = 0; j < 4; j++) {
-                            u32 t7 = ((w[j] ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                            u32 t7 = ((w[j] ^ c0a) & c7f) + c7f;
                             u32 f = ~(t7 | w[j]) & 0x80808080u;            // 0x80 where the byte is '\n' (exact)
                             m = __funnelshift_r(m, __umulhi(f, 0x02040810u), 4);
                         }

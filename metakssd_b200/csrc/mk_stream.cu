@@ -243,10 +243,12 @@ __device__ __forceinline__ u32 shr_fma(u32 x) { return x >> SH; }
 // 16 ASCII bases -> 32 bits, base i at bits [2i, 2i+2) (garbage for non-ACGT bytes, by design)
 __device__ __forceinline__ u32 pack16(uint4 v)
 {
-    u32 x0 = ((shr_fma<1>(v.x) ^ shr_fma<2>(v.x)) & 0x03030303u) * 0x01041040u;
-    u32 x1 = ((shr_fma<1>(v.y) ^ shr_fma<2>(v.y)) & 0x03030303u) * 0x01041040u;
-    u32 x2 = ((shr_fma<1>(v.z) ^ shr_fma<2>(v.z)) & 0x03030303u) * 0x01041040u;
-    u32 x3 = ((shr_fma<1>(v.w) ^ shr_fma<2>(v.w)) & 0x03030303u) * 0x01041040u;
+    // code = ((c >> 1) ^ (c >> 2)) & 3 = ((c ^ (c >> 1)) >> 1) & 3: one shift, one LOP3; the remaining
+    // ">> 1" is folded into the gathering multiplier (0x01041040 >> 1)
+    u32 x0 = ((v.x ^ shr_fma<1>(v.x)) & 0x06060606u) * 0x00820820u;
+    u32 x1 = ((v.y ^ shr_fma<1>(v.y)) & 0x06060606u) * 0x00820820u;
+    u32 x2 = ((v.z ^ shr_fma<1>(v.z)) & 0x06060606u) * 0x00820820u;
+    u32 x3 = ((v.w ^ shr_fma<1>(v.w)) & 0x06060606u) * 0x00820820u;
     return __byte_perm(__byte_perm(x0, x1, 0x0073), __byte_perm(x2, x3, 0x7300), 0x7610);
 }
 
@@ -1166,7 +1168,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 u32 m0 = 0, m1 = 0;
                 if (off < TB) {
                     const uint4 *q = reinterpret_cast<const uint4 *>(tx + MK_HALO + off);
-                    const u32 rot = (lane >> 1) & 3u;           // conflict-free piece order (plain order: -1 %)
+                    // The four 16-byte pieces are read in a per-lane rotated order (conflict-free; plain
+                    // order costs 1 %); piece k4 of the loop is piece (k4 + rot) & 3 of the 64 bytes, so the
+                    // 64-bit mask is the loop-order concatenation rotated left by 16 rot bits.
+                    const u32 rot = (lane >> 1) & 3u;
+                    u32 r[4];
 #pragma unroll
                     for (int k4 = 0; k4 < 4; k4++) {
                         const u32 pc = (k4 + rot) & 3u;
@@ -1179,10 +1185,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                             u32 f = ~(t7 | w[j]) & 0x80808080u;            // 0x80 where the byte is '\n' (exact)
                             m = __funnelshift_r(m, __umulhi(f, 0x02040810u), 4);
                         }
-                        m >>= 16;
-                        m <<= (pc & 1u) * 16u;
-                        if (pc & 2u) m1 |= m; else m0 |= m;
+                        r[k4] = m;                                        // the piece's 16 bits sit in the top half
                     }
+                    u32 lo = __byte_perm(r[0], r[1], 0x7632), hi = __byte_perm(r[2], r[3], 0x7632);
+                    if (rot & 2u) { const u32 t = lo; lo = hi; hi = t; }
+                    const u32 sh = (rot & 1u) * 16u;
+                    m0 = __funnelshift_l(hi, lo, sh);
+                    m1 = __funnelshift_l(lo, hi, sh);
                 }
                 const u32 c0 = __popc(m0), cnt = c0 + __popc(m1);
                 u32 incl = cnt;

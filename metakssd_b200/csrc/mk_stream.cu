@@ -1250,11 +1250,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                             const u32 nl = G.nlm[b];
                             const u32 s0 = (P + G.cpre[b >> 6] + G.exw[b]) & 3u;
                             const u32 tgt = (1u - s0) & 3u;
-                            u32 p0 = 0, p1 = 0;
-                            if (nl) {
-                                p0 = prefix_xor(nl << 1);
-                                p1 = prefix_xor((nl & p0) << 1);
-                            }
+                            // (no "if (nl)": some lane of the warp always has a newline, the branch only costs)
+                            const u32 p0 = prefix_xor(nl << 1);
+                            const u32 p1 = prefix_xor((nl & p0) << 1);
                             pm[h] = (p0 ^ ((tgt & 1u) ? 0u : ~0u)) & (p1 ^ ((tgt & 2u) ? 0u : ~0u)) & ~nl;
                         }
                         G.nlm[b] = pm[h];

@@ -145,9 +145,8 @@ extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int 
             word = (u32)(q >> 2) & wm; bit = (u32)(q >> (MK_BLOOM_WBITS + 2)) & 31u;
             bitmap[word] |= 1u << (31 - bit);
             word = (u32)(q >> 6) & wm;
-            bit = ((u32)(q >> (6 + MK_BLOOM_WBITS)) & ((1u << MK_BLOOM_TOPBITS) - 1u)) |
-                  (((u32)q & ((1u << (5 - MK_BLOOM_TOPBITS)) - 1u)) << MK_BLOOM_TOPBITS);
-            bitmap[word] |= 1u << (31 - bit);
+            bit = ((u32)(q >> 19) ^ (u32)q) & 31u;
+            bitmap[word] |= 1u << bit;                     // (natural bit order for the second hash)
         } else {
             word = (u32)(q & ((1ull << (K.mw - 5)) - 1)); bit = (u32)(q >> (K.mw - 5)) & 31u;
             bitmap[word] |= 1u << (31 - bit);

@@ -315,7 +315,7 @@ __device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, in
 }
 
 // Second hash of the two-hash Bloom filter (inner windows of 22 bits or more): word from window bits
-// 6..5+MK_BLOOM_WBITS, bit from the window bits above them and the lowest bits (the first hash uses
+// 6..5+MK_BLOOM_WBITS, bit from window bits 19..23 xor-ed onto the lowest five bits (the first hash uses
 // bits 2..6+MK_BLOOM_WBITS).  Must mirror set_bit() in
 // mk_api.cu.
 __device__ __forceinline__ bool second_hash_hit(const u32 (&A)[4], u32 j, const u32 *bm)
@@ -324,8 +324,9 @@ __device__ __forceinline__ bool second_hash_hit(const u32 (&A)[4], u32 j, const 
     u32 hi = j < 16 ? A[1] : A[2];
     u32 v = __funnelshift_r(lo, hi, (2 * j) & 31);
     u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + ((v >> 4) & (((1u << MK_BLOOM_WBITS) - 1u) << 2)));
-    u32 bit = ((v >> (6 + MK_BLOOM_WBITS)) & ((1u << MK_BLOOM_TOPBITS) - 1u)) | ((v & ((1u << (5 - MK_BLOOM_TOPBITS)) - 1u)) << MK_BLOOM_TOPBITS);
-    return (word >> (31u - bit)) & 1u;
+    // bit index: window bits 19..23 folded onto bits 0..4 (bits 0 and 1 are the ones the first hash does
+    // not see); stored in natural order (bit b <-> 1 << b), unlike the first hash's rotate trick
+    return (word >> (((v >> 19) ^ v) & 31u)) & 1u;        // (v carries more than the 24 window bits: only bits < 24 may be used)
 }
 
 // A position that passed the shared-memory filter: appended to the global hit list; k_verify turns
@@ -1322,6 +1323,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             const uint8_t *tx = tbuf + s * WS_TBUF;
             const u64 T = (u64)t * TB;
             const u32 n = S.n_items[s];
+            const bool two_hash = A.two_hash != 0;
             for (u32 r = pw >= rot ? pw - rot : pw + WS_NPW - rot; r * 32u < n; r += WS_NPW) {
                 const u32 it = r * 32u + lane;
                 if (it < n) {
@@ -1332,7 +1334,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                     while (hits) {
                         u32 j = __ffs(hits) - 1;
                         hits &= hits - 1;
-                        if (A.two_hash && !second_hash_hit(Aw, j, bm)) continue;
+                        if (two_hash && !second_hash_hit(Aw, j, bm)) continue;
                         emit_hit(A, T + 32 * b + j);
                     }
                 }

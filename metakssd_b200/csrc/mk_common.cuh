@@ -17,7 +17,6 @@ typedef unsigned int u32;
 #ifndef MK_BLOOM_WBITS
 #define MK_BLOOM_WBITS 15
 #endif
-#define MK_BLOOM_TOPBITS (24 - 6 - MK_BLOOM_WBITS)   // window bits above the second hash's word index
 #define MK_HALO 32            // bytes of left context staged in front of every text tile
 #define MK_MAX_TILE 24576     // tile-proper bytes (multiple of 64); three stages fit beside the bitmap
 #ifndef MK_STREAM_THREADS

@@ -300,3 +300,16 @@ def test_long_lines_exact_threshold(oracle, sk311):
             s.fastq_koc_host(np.frombuffer(text, np.uint8).copy())
         assert e.value.code == -6, (seq_len, where, e.value)   # MK_ERR_LONG_LINE
 
+
+def test_classic_stream_kernel_agrees(oracle, sk311, monkeypatch):
+    """MK_STREAM_IMPL=classic selects the earlier unit-pulling kernel (kept as a cross-check of the
+    warp-specialised one): same sketch, from device and from host text."""
+    s, perm, p = sk311
+    S = oracle.synth(31, 15, 150000, 150)
+    text = S.fastq(0, 30000)
+    want = oracle.fastq_koc(p, perm, text)
+    monkeypatch.setenv("MK_STREAM_IMPL", "classic")
+    same_sketch(s.fastq_koc_host(text), want, p)
+    monkeypatch.delenv("MK_STREAM_IMPL")
+    same_sketch(s.fastq_koc_host(text), want, p)
+

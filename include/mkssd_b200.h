@@ -47,7 +47,8 @@ extern "C" {
 #define MK_ERR_LONG_LINE (-6)   /* FASTQ line >= 4095 bytes: fgets(…,4096) splitting in the
                                    reference is input-buffer dependent; refused                 */
 #define MK_ERR_IO (-7)          /* popen/fopen/read failure                                      */
-#define MK_ERR_EMPTY_QUERY (-8) /* composite with 0 query codes (reference: modulo by zero)      */
+#define MK_ERR_EMPTY_QUERY (-8) /* composite query component of exactly 1 code (reference: modulo by
+                                   zero, command_composite.c:535; 0 codes = no hits, not an error)  */
 #define MK_ERR_UNSUPPORTED (-9)
 
 typedef struct mk_ctx mk_ctx;

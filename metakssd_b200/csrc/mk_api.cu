@@ -1,5 +1,6 @@
 // mk_api.cu — extern "C" entry points of libmkssd_b200.so (see include/mkssd_b200.h).
 #include "mk_common.cuh"
+#include "mk_stream3.cuh"
 #include <limits.h>
 #include <errno.h>
 #include <new>
@@ -31,7 +32,7 @@ extern "C" const char *mk_strerror(int code)
     case MK_ERR_CROWDED: return "the context space is too crowd";
     case MK_ERR_LONG_LINE: return "FASTQ line of 4095 bytes or more";
     case MK_ERR_IO: return "I/O error";
-    case MK_ERR_EMPTY_QUERY: return "composite query sketch is empty";
+    case MK_ERR_EMPTY_QUERY: return "composite query component with exactly one code";
     case MK_ERR_UNSUPPORTED: return "unsupported configuration";
     default: return "unknown error";
     }
@@ -137,6 +138,7 @@ extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int 
     else bm_words = 1u << (K.mw - 5);               // exact bitmap (128 KB at mw = 20)
     if (bm_words < 4) bm_words = 4;
     std::vector<u32> bitmap(bm_words, 0);
+    std::vector<u32> bitmap3((size_t)1 << mk_s3_word_bits(K.mw), 0);
     // mw >= 22: two-hash Bloom filter in 2^(MK_BLOOM_WBITS+5) bits; mw <= 20: exact bitmap.  Mirrors probe_block()/second_hash_hit().
     auto set_bit = [&](u64 q) {
         u32 word, bit;
@@ -163,10 +165,16 @@ extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int 
         }
         set_bit(pair_reverse(d, 2 * subk));   // forward strand is canonical
         set_bit((~d) & mwmask);               // reverse complement is canonical
+        mk_s3_filter_add(bitmap3, K.mw, pair_reverse(d, 2 * subk));
+        mk_s3_filter_add(bitmap3, K.mw, (~d) & mwmask);
     }
     ctx->bitmap_words = bm_words;
     if (cudaMalloc(&ctx->d_bitmap, (size_t)bm_words * 4) != cudaSuccess) return fail(MK_ERR_NOMEM);
     if (cudaMalloc(&ctx->d_ptab, tcap * 8) != cudaSuccess) return fail(MK_ERR_NOMEM);
+    ctx->bitmap3_words = (u32)bitmap3.size();
+    if (cudaMalloc(&ctx->d_bitmap3, bitmap3.size() * 4) != cudaSuccess) return fail(MK_ERR_NOMEM);
+    if (cudaMemcpy(ctx->d_bitmap3, bitmap3.data(), bitmap3.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess)
+        return fail(MK_ERR_CUDA);
     if (cudaMemcpy(ctx->d_bitmap, bitmap.data(), (size_t)bm_words * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(ctx->d_ptab, ptab.data(), tcap * 8, cudaMemcpyHostToDevice) != cudaSuccess)
         return fail(MK_ERR_CUDA);
@@ -182,6 +190,7 @@ extern "C" void mk_ctx_destroy(mk_ctx *ctx)
     for (int i = 0; i < SB_NUM; i++)
         if (ctx->sb[i].p) cudaFree(ctx->sb[i].p);
     if (ctx->d_bitmap) cudaFree(ctx->d_bitmap);
+    if (ctx->d_bitmap3) cudaFree(ctx->d_bitmap3);
     if (ctx->d_ptab) cudaFree(ctx->d_ptab);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     mk_markerdb_unload(ctx);

@@ -51,7 +51,7 @@ enum {
     SB_OUT_KEY, SB_SEG_COUNTS, SB_TEXT, SB_SCAN_TMP, SB_FA_STATE, SB_FA_CNT, SB_FA_DENSE, SB_FA_OFF,
     SB_CQ_KEYS, SB_CQ_IDX, SB_C_REF, SB_C_IDX, SB_C_QRY, SB_C_QCNT, SB_C_HITVAL, SB_C_POS, SB_C_STORE_S,
     SB_C_STORE_C, SB_C_STATS, SB_C_NH, SB_SYN_CDF, SB_SYN_SPC, SB_MISC, SB_FILE_OFF, SB_RUN_CODE,
-    SB_RUN_POS, SB_RUN_CNT, SB_NUM
+    SB_RUN_POS, SB_RUN_CNT, SB_TILE_DESC8, SB_S3_ARENA, SB_NUM
 };
 
 struct ResidentComponent {         // one MarkerDB component kept on the device (mk_markerdb_load)
@@ -72,6 +72,8 @@ struct mk_ctx {
     KParams kp;
     u32 *d_bitmap = nullptr;
     u32 bitmap_words = 0;
+    u32 *d_bitmap3 = nullptr;       // two-plane core filter of k_stream3 (mk_stream3.cu)
+    u32 bitmap3_words = 0;
     u64 *d_ptab = nullptr;
     void *d_trace = nullptr;        // development aid: phase timestamps of CTA 0 (mk_debug_set_trace)
     Scratch sb[SB_NUM];

@@ -88,12 +88,14 @@ static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uin
 {
     CK(cudaSetDevice(ctx->device));
     const u64 q = qry_hi - qry_lo;
-    // the reference sizes its dictionary with nextPrime((int)(q / 0.6)); 0 or 1 make it divide by zero
-    if ((int)((double)q / 0.6) <= 1) {
-        snprintf(ctx->err, sizeof(ctx->err), "composite: query sketch has %llu codes", (unsigned long long)q);
+    // The reference sizes its dictionary with nextPrime((int)(q / 0.6)) (command_composite.c:535).  q == 0 gives
+    // a table of 0 slots: both loops run zero times, the component contributes no hits and the run goes on.
+    // q == 1 gives 1 slot and HASH() then takes K % (hash_sz - 1) = K % 0: the reference dies with SIGFPE.
+    if (q == 0 || r == 0) return MK_OK;
+    if (q == 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "composite: query component with exactly one code (the reference divides by zero)");
         return MK_ERR_EMPTY_QUERY;
     }
-    if (r == 0) return MK_OK;
     if (r >= 0xFFFFFFFFull || q >= 0x7FFFFFFFull) return MK_ERR_UNSUPPORTED;
     cudaEvent_t e0 = ctx->ev2, e1 = ctx->ev3;
     CK(cudaEventRecord(e0, ctx->stream));

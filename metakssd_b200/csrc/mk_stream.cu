@@ -18,114 +18,9 @@
 //     from the text (22 valid ACGT bytes inside one line, canonical strand, exact table), so the
 //     fast path is: 2 funnel shifts, 1 AND, 1 LDS, 2 funnel shifts per position.
 #include "mk_common.cuh"
+#include "mk_stream_dev.cuh"
+#include "mk_stream3.cuh"
 
-struct StreamArgs {
-    const uint8_t *text;
-    u64 nbytes;
-    u64 pos_base;
-    u64 line_base;
-    u32 tile_bytes;
-    u32 n_tiles;            // tiles [tile_begin, n_tiles) are processed by this launch
-    u32 tile_begin;         // multiple of the ticket group size (k_stream_ws; 0 for a whole-text launch)
-    const u64 *line_base_ptr;   // optional: added to line_base (total of the launch before, chunked host path)
-    u64 *tile_desc;
-    u32 *tile_counter;
-    u32 *count_counter;     // tickets of the count-ahead pass (k_stream_ws)
-    const u32 *bitmap;
-    u32 bitmap_bytes;
-    const u64 *ptab;
-    u32 two_hash;           // 1: the bitmap is a two-hash Bloom filter (inner window of 22+ bits)
-    u64 *cand_code;
-    u64 *cand_pos;
-    u64 *cand_count;
-    u64 cand_cap;
-    u32 *flags;
-    u64 *total_newlines;
-    u64 *trace;             // optional per-warp phase timestamps of CTA 0 (development aid)
-    u64 *wd;                // watchdog diagnostics: [site, block, warp, a, b, c, d, e]
-    KParams kp;
-};
-
-#define TBUF_STRIDE (MK_HALO + MK_MAX_TILE + 96) // keeps the stage buffers 128-byte aligned
-#define FLAG_LONG_LINE 2u
-#define FLAG_MAYBE_LONG 8u   // some 2 KB chunk holds no newline: the host runs the exact line-length check
-#define FLAG_WATCHDOG 4u     // a wait inside k_stream gave up (diagnostics in StreamArgs::wd)
-#define WD_LIMIT (1u << 21)
-
-// ---- PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ u32 smem_u32(const void *p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(u64 *bar, u32 count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-#ifndef MK_WAIT_HINT
-#define MK_WAIT_HINT 2000       // try_wait suspend-time hint (ns); small enough that the poll-count watchdog still fires within seconds
-#endif
-__device__ __forceinline__ u32 mbar_try_wait(u64 *bar, u32 parity)
-{
-    u32 ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"((u32)MK_WAIT_HINT)
-        : "memory");
-    return ok;
-}
-// false = gave up (the caller raises the watchdog flag); every failed try_wait suspends the warp for
-// a short hardware-defined time, so the loop is kept to the bare minimum of instructions
-__device__ __forceinline__ bool mbar_wait(u64 *bar, u32 parity)
-{
-    for (u32 n = 0; !mbar_try_wait(bar, parity); n++)
-        if (n > WD_LIMIT) return false;
-    return true;
-}
-__device__ __forceinline__ void named_bar_sync(u32 id, u32 nthreads)
-{
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async()
-{
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, u32 bytes, u64 *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// same, with an L2 evict_first hint: the text is not needed again once it sits in shared memory
-__device__ __forceinline__ void tma_load_1d_last_use(void *dst, const void *src, u32 bytes, u64 *bar)
-{
-    asm volatile("{\n\t.reg .b64 pol;\n\tcreatepolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
-                 "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], pol;\n\t}" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ u64 ld_volatile_u64(const u64 *p)
-{
-    u64 v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_volatile_u64(u64 *p, u64 v)
-{
-    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ u64 warp_sum_u64(u64 v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // 512-thread exclusive scan (two barriers); ws holds 16 warp slots + total
 __device__ __forceinline__ u32 block_excl_scan_512(u32 v, u32 *ws /*[17]*/, u32 *total)
@@ -225,42 +120,6 @@ __device__ __forceinline__ bool verify_kmer(const uint8_t *t, const KParams &kp,
     return true;
 }
 
-// The probe is bound by the integer ALU pipe (shifts, logic); the FMA pipe, which also executes
-// IMAD / IMAD.HI, is mostly idle.  Right shifts by a compile-time amount are therefore written as
-// "high half of a multiply by 2^(32-s)" so that ptxas places them on the FMA pipe.
-#ifndef MK_ALU_SHIFTS
-template <int SH>
-__device__ __forceinline__ u32 shr_fma(u32 x)
-{
-    if (SH == 0) return x;
-    return __umulhi(x, 1u << ((32 - SH) & 31));
-}
-#else
-template <int SH>
-__device__ __forceinline__ u32 shr_fma(u32 x) { return x >> SH; }
-#endif
-
-// 16 ASCII bases -> 32 bits, base i at bits [2i, 2i+2) (garbage for non-ACGT bytes, by design)
-__device__ __forceinline__ u32 pack16(uint4 v)
-{
-    // code = ((c >> 1) ^ (c >> 2)) & 3 = ((c ^ (c >> 1)) >> 1) & 3: one shift, one LOP3; the remaining
-    // ">> 1" is folded into the gathering multiplier (0x01041040 >> 1)
-    u32 x0 = ((v.x ^ shr_fma<1>(v.x)) & 0x06060606u) * 0x00820820u;
-    u32 x1 = ((v.y ^ shr_fma<1>(v.y)) & 0x06060606u) * 0x00820820u;
-    u32 x2 = ((v.z ^ shr_fma<1>(v.z)) & 0x06060606u) * 0x00820820u;
-    u32 x3 = ((v.w ^ shr_fma<1>(v.w)) & 0x06060606u) * 0x00820820u;
-    return __byte_perm(__byte_perm(x0, x1, 0x0073), __byte_perm(x2, x3, 0x7300), 0x7610);
-}
-
-// window extraction for position J: 32 bits of the packed bases starting at bit offset O; only
-// bits [0, NEED) of the result are used, which lets single-word cases run on the FMA pipe.
-template <int O, int NEED>
-__device__ __forceinline__ u32 take_bits(const u32 (&A)[4])
-{
-    constexpr int W = O >> 5, SH = O & 31;
-    if (SH + NEED <= 32) return shr_fma<SH>(A[W]);
-    return __funnelshift_r(A[W], A[W + 1], SH);
-}
 
 template <int ROTOFF, u32 WORDMASK, int J>
 __device__ __forceinline__ void probe_one(const u32 (&A)[4], const u32 *bm, u32 &hits)
@@ -329,13 +188,6 @@ __device__ __forceinline__ bool second_hash_hit(const u32 (&A)[4], u32 j, const 
     return (word >> (((v >> 19) ^ v) & 31u)) & 1u;        // (v carries more than the 24 window bits: only bits < 24 may be used)
 }
 
-// A position that passed the shared-memory filter: appended to the global hit list; k_verify turns
-// it into a (code, position) candidate or drops it.
-__device__ __forceinline__ void emit_hit(const StreamArgs &A, u64 pos)
-{
-    u64 idx = atomicAdd((unsigned long long *)A.cand_count, 1ull);
-    if (idx < A.cand_cap) A.cand_pos[idx] = pos;
-}
 
 #define MAXBLK (MK_MAX_TILE / 32)
 #define MAXCHUNK (MK_MAX_TILE / 2048)   // scan chunks: one warp pass = 32 lanes x 64 bytes
@@ -809,10 +661,6 @@ struct WsSmem {
     u32 tile[NS], n_items[NS], scnt[NS];
 };
 
-__device__ __forceinline__ void prefetch_l2(const void *p, u32 bytes)
-{
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
 #ifndef WS_CNT_BATCH
 #define WS_CNT_BATCH 12 // 16-byte loads in flight per lane of a count warp
 #endif
@@ -831,19 +679,9 @@ __device__ __forceinline__ uint4 ld_nc_u128(const void *p)
 #endif
     return v;
 }
-__device__ __forceinline__ u32 ld_volatile_u32(const u32 *p)
-{
-    u32 v;
-    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ void ld_volatile_v2(const u64 *p, u32 &lo, u32 &hi)
 {
     asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(u64 *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // cold path, kept out of line so that the roles' loops stay compact in the instruction cache
@@ -1541,16 +1379,18 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         return MK_ERR_ARG;
     }
     const KParams &kp = ctx->kp;
-    // MK_STREAM_IMPL=classic selects the unit-pulling kernel (k_stream); default: warp-specialised
+    // MK_STREAM_IMPL selects the kernel: default k_stream_ws (warp-specialised ring); "v3" = k_stream3 (front
+    // end ahead of the ring, mk_stream3.cu) and "classic" = the unit-pulling kernel, both kept as cross-checks
     const char *impl = getenv("MK_STREAM_IMPL");
-    const bool ws = !(impl && !strcmp(impl, "classic"));
-    stream_kernel_t kern = ws ? pick_kernel_ws(kp, raw_mode) : pick_kernel(kp, raw_mode);
-    if (!kern) {
+    const bool v3 = impl && !strcmp(impl, "v3");
+    const bool ws = v3 || !(impl && !strcmp(impl, "classic"));      // (v3 shares the chunked-upload path with ws)
+    stream_kernel_t kern = v3 ? nullptr : (ws ? pick_kernel_ws(kp, raw_mode) : pick_kernel(kp, raw_mode));
+    if (!kern && !v3) {
         snprintf(ctx->err, sizeof(ctx->err), "unsupported inner substring width subk=%d", kp.subk);
         return MK_ERR_UNSUPPORTED;
     }
     // tile-proper bytes: a multiple of 64 (two 32-byte probe blocks per scanning thread)
-    const u32 max_tile = ws ? (u32)WS_TILE : (u32)MK_MAX_TILE;
+    const u32 max_tile = v3 ? (u32)S3_TILE : (ws ? (u32)WS_TILE : (u32)MK_MAX_TILE);
     u32 tile_bytes = raw_mode ? (max_tile < 16384u ? max_tile : 16384u) : max_tile;
     if (const char *e = getenv(raw_mode ? "MK_RAW_TILE_BYTES" : "MK_TILE_BYTES")) {
         u32 v = (u32)atoi(e);
@@ -1570,8 +1410,19 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     double rate = 2.0 * (double)kp.dim_end / (double)(1ull << (4 * kp.subk)) + 0.003;
     if (rate > 1.0) rate = 1.0;
     u64 cap = (u64)((double)nbytes * rate * 0.75) + 65536;
-    size_t smem = ws ? stream_smem_bytes_ws(ctx->bitmap_words * 4, ws_stages(kp)) : stream_smem_bytes(ctx->bitmap_words * 4);
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    size_t smem = 0;
+    if (!v3) {
+        smem = ws ? stream_smem_bytes_ws(ctx->bitmap_words * 4, ws_stages(kp)) : stream_smem_bytes(ctx->bitmap_words * 4);
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    uint8_t *desc8 = nullptr;
+    u64 *ttab = nullptr;
+    size_t arena_items = v3 ? mk_s3_arena_items(nbytes, tile_bytes) : 0;
+    if (v3) {
+        CKR(mk_scratch(ctx, SB_TILE_DESC8, (size_t)n_tiles + 64, &desc8));
+        CKR(mk_scratch(ctx, SB_TILE_DESC, (size_t)n_tiles, &ttab));
+    }
+    const u32 group = v3 ? 1u : (u32)WS_G;      // launches of the chunked path start on a ticket-group boundary
 
     // Host source pending (mk_fastq_koc_host): upload and sketch in chunks, the copy of chunk i+1 under
     // the kernel of chunk i.  Each chunk is one launch over its tile range; the line count carries over
@@ -1590,12 +1441,36 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     if (ctx->h_src_all && !h_src) { CKR(upload_all()); }
     ctx->h_src_all = nullptr;
 
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 3; attempt++) {
         u64 *cc, *cp;
         CKR(mk_scratch(ctx, SB_CAND_CODE, (size_t)cap, &cc));
         CKR(mk_scratch(ctx, SB_CAND_POS, (size_t)cap, &cp));
-        CK(cudaMemsetAsync(desc, 0, (size_t)n_tiles * 8, ctx->stream));
+        u32 *arena = nullptr;
+        if (v3) {
+            CKR(mk_scratch(ctx, SB_S3_ARENA, arena_items, &arena));
+            CK(cudaMemsetAsync(desc8, 0, (size_t)n_tiles + 64, ctx->stream));
+            CK(cudaMemsetAsync(ttab, 0, (size_t)n_tiles * 8, ctx->stream));
+        } else CK(cudaMemsetAsync(desc, 0, (size_t)n_tiles * 8, ctx->stream));
         CK(cudaMemsetAsync(counters, 0, 128, ctx->stream));
+        S3Args a3;
+        a3.text = d_text; a3.nbytes = nbytes; a3.line_base = line_base; a3.tile_bytes = tile_bytes;
+        a3.n_tiles = n_tiles; a3.tile_begin = 0; a3.desc = desc8;
+        a3.flags = (u32 *)(counters + 2) + 1;
+        a3.ttab = ttab; a3.arena = arena; a3.arena_cap = arena_items; a3.arena_cursor = counters + 7;
+        a3.bitmap = ctx->d_bitmap3; a3.bitmap_bytes = ctx->bitmap3_words * 4;
+        a3.cand_count = counters + 0; a3.total_newlines = counters + 1; a3.wd = counters + 8;
+        a3.TL = kp.TL;
+        a3.stats = nullptr; a3.stat_cta = 0;
+#ifdef S3_STATS
+        u64 *d_stats = nullptr;
+        if (getenv("MK_S3_STATS")) {
+            CKR(mk_scratch(ctx, SB_MISC, 128, &d_stats));
+            CK(cudaMemsetAsync(d_stats, 0, 128 * 8, ctx->stream));
+            a3.stats = d_stats;
+            a3.stat_cta = (u32)atoi(getenv("MK_S3_STATS"));
+        }
+#endif
+        a3.prew = (kp.pre + 15) / 16; a3.shift_d = 2 * (16 * a3.prew - kp.pre);
         StreamArgs a;
         a.text = d_text; a.nbytes = nbytes; a.pos_base = pos_base; a.line_base = line_base;
         a.tile_bytes = tile_bytes; a.n_tiles = n_tiles; a.tile_begin = 0; a.line_base_ptr = nullptr; a.tile_desc = desc;
@@ -1604,14 +1479,15 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         a.count_counter = (u32 *)(counters + 3);
         a.bitmap = ctx->d_bitmap; a.bitmap_bytes = ctx->bitmap_words * 4; a.ptab = ctx->d_ptab; a.two_hash = ctx->kp.mw >= 22 ? 1u : 0u;
         a.cand_code = cc; a.cand_pos = cp; a.cand_cap = cap; a.kp = kp; a.trace = (u64 *)ctx->d_trace; a.wd = counters + 8;
+        a3.cand_pos = cp; a3.cand_cap = cap;
         const u32 threads = ws ? WS_THREADS : MK_STREAM_THREADS;
         u64 *total_slot = counters + 1;
         CK(cudaEventRecord(ctx->ev0, ctx->stream));
         if (h_src && attempt == 0) {
             size_t chunk_bytes = (size_t)192 << 20;
             if (const char *e = getenv("MK_CHUNK_BYTES")) chunk_bytes = (size_t)atoll(e);   // (tests: force many chunks)
-            u32 tiles_per_chunk = (u32)(chunk_bytes / tile_bytes) / WS_G * WS_G;
-            if (tiles_per_chunk < WS_G) tiles_per_chunk = WS_G;
+            u32 tiles_per_chunk = (u32)(chunk_bytes / tile_bytes) / group * group;
+            if (tiles_per_chunk < group) tiles_per_chunk = group;
             const u32 nchunk = (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk;
             while (ctx->chunk_ev.size() < nchunk) {
                 cudaEvent_t e;
@@ -1639,16 +1515,25 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
                 a.total_newlines = total_slot;
                 const u32 nt = t1 - t0;
                 const u32 grid = nt < (u32)ctx->sm_count ? nt : (u32)ctx->sm_count;
+                if (v3) {       // (line phase and newline total carry over through the tile descriptors / the counter)
+                    a3.tile_begin = t0; a3.n_tiles = t1;
+                    CKR(mk_s3_launch(ctx, a3, raw_mode, grid));
+                } else {
+                    kern<<<grid, threads, smem, ctx->stream>>>(a);
+                    LAUNCH_COUNT(ctx);
+                    CK(cudaGetLastError());
+                }
+            }
+            if (v3) total_slot = counters + 1;
+            ctx->prof.h2d_bytes += nbytes;
+        } else {
+            u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
+            if (v3) CKR(mk_s3_launch(ctx, a3, raw_mode, grid));
+            else {
                 kern<<<grid, threads, smem, ctx->stream>>>(a);
                 LAUNCH_COUNT(ctx);
                 CK(cudaGetLastError());
             }
-            ctx->prof.h2d_bytes += nbytes;
-        } else {
-            u32 grid = n_tiles < (u32)ctx->sm_count ? n_tiles : (u32)ctx->sm_count;
-            kern<<<grid, threads, smem, ctx->stream>>>(a);
-            LAUNCH_COUNT(ctx);
-            CK(cudaGetLastError());
         }
         CK(cudaEventRecord(ctx->ev1, ctx->stream));
         u64 h[16];
@@ -1660,6 +1545,20 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         ctx->prof.stream_kernel_ms += ms;
         ctx->prof.stream_kernel_launches++;
         ctx->prof.stream_kernel_bytes += nbytes;
+#ifdef S3_STATS
+        if (a3.stats) {
+            u64 st[128];
+            CK(cudaMemcpy(st, a3.stats, sizeof(st), cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[s3 hist, 8K-cycle bins] scan:");
+            for (int i = 0; i < 16; i++) fprintf(stderr, " %llu", st[32 + i]);
+            fprintf(stderr, " | lookback:");
+            for (int i = 0; i < 16; i++) fprintf(stderr, " %llu", st[48 + i]);
+            fprintf(stderr, "\n");
+            fprintf(stderr, "[s3 stats, CTA %u, kilo-cycles] loader: free-wait %llu (%llu waits) | dispatcher (%llu items): table-wait %llu full-wait %llu room-wait %llu | front (%llu tiles, %llu items): ahead-wait %llu scan %llu lookback %llu (%llu retries, %llu windows) emit %llu publish %llu loop-total %llu | probe (%llu claims, %llu items): claim-wait %llu work %llu\n",
+                    a3.stat_cta, st[0] / 1000, st[1], st[27], st[24] / 1000, st[25] / 1000, st[26] / 1000, st[9], st[13], st[8] / 1000, st[10] / 1000,
+                    st[11] / 1000, st[20], st[21], st[12] / 1000, st[15] / 1000, st[14] / 1000, st[17], st[18], st[16] / 1000, st[19] / 1000);
+        }
+#endif
         u32 flags = (u32)(h[2] >> 32);
         if (flags & FLAG_WATCHDOG) {
             snprintf(ctx->err, sizeof(ctx->err),
@@ -1669,6 +1568,10 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
                      (unsigned long long)h[14], (unsigned long long)(h[15] >> 42),
                      (unsigned long long)((h[15] >> 21) & 0x1FFFFF), (unsigned long long)(h[15] & 0x1FFFFF), n_tiles);
             return MK_ERR_CUDA;
+        }
+        if (v3 && (flags & FLAG_ARENA_FULL)) {       // unusually many short sequence lines: the cursor says what is needed
+            arena_items = (size_t)h[7] + 1024;
+            continue;
         }
         bool long_line = !raw_mode && (flags & FLAG_LONG_LINE);
         if (!raw_mode && !long_line && (flags & FLAG_MAYBE_LONG)) {     // rare: measure the line exactly
@@ -1694,7 +1597,7 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
             CK(cudaGetLastError());
         }
         *n_cand = h[0];
-        if (n_newlines) *n_newlines = raw_mode ? line_base : h[total_slot - counters];
+        if (n_newlines) *n_newlines = raw_mode ? line_base : (v3 ? line_base + h[1] : h[total_slot - counters]);
         *d_cand_code = cc;
         *d_cand_pos = cp;
         return MK_OK;

@@ -320,13 +320,15 @@ static int next_prime_int(int n)
 /* command_composite.c:535-566 for ONE (query, component): builds the query dictionary with the
  * reference's 32-bit wrap-around probe arithmetic and appends, per species, the query count of
  * every MarkerDB code found.  hits[s] must have room for (ref_index[s+1]-ref_index[s]) values;
- * nhits[s] is incremented.  Returns 0, or -1 for an empty query (reference: modulo by zero). */
+ * nhits[s] is incremented.  Returns 0, or -1 for a query component of exactly one code (reference:
+ * modulo by zero); an empty component yields no hits like in the reference. */
 int ko_composite_component(const uint32_t *ref_codes, const size_t *ref_index, int n_species,
                            const uint32_t *qry_codes, const uint16_t *qry_counts, size_t q_lo,
                            size_t q_hi, int32_t **hits, int32_t *nhits)
 {
     int hash_sz = next_prime_int((int)((double)(q_hi - q_lo) / 0.6));
-    if (hash_sz <= 1) return -1;
+    if (hash_sz == 0) return 0;    /* empty query component: both loops of the reference run zero times */
+    if (hash_sz == 1) return -1;   /* one code: HASH() takes K % (hash_sz - 1) = K % 0, the reference dies with SIGFPE */
     size_t *dict = (size_t *)calloc((size_t)hash_sz, sizeof(size_t));
     if (!dict) return -2;
     for (size_t idx = q_lo; idx < q_hi; idx++) {

@@ -140,11 +140,13 @@ static int cmd_dist(int argc, char **argv)
 
     static const char *const fq_ext[] = {"fq", "fastq", NULL};
     mk_sketch *sk = calloc((size_t)n_in, sizeof *sk);
-    for (int i = 0; i < n_in; i++) {
+    for (int i = 0; i < n_in;) {
         bool fq = has_ext(inputs[i], fq_ext) || pipecmd[0];
         if (fq && abundance) {
             printf("running mt_shortreads2koc()\n");
             ck(ctx, mk_fastq_koc_file(ctx, inputs[i], pipecmd, &sk[i]), inputs[i]);
+            printf("%d/%d decomposing %s\r", i + 1, n_in, inputs[i]);
+            i++;
         } else if (fq) {
             die("FASTQ without -A is outside the accelerated path", inputs[i]);
         } else {
@@ -152,9 +154,13 @@ static int cmd_dist(int argc, char **argv)
                 abundance = false;
                 printf("Warning: close abundance mode (-A) since non-fastq file input.\n");
             }
-            ck(ctx, mk_fasta_co_file(ctx, inputs[i], pipecmd, &sk[i]), inputs[i]);
+            /* the file loop of run_stageI() (command_dist.c:365) as one batched call over the run of genomes */
+            int j = i;
+            while (j < n_in && !(has_ext(inputs[j], fq_ext) || pipecmd[0])) j++;
+            ck(ctx, mk_fasta_co_files(ctx, (const char *const *)(inputs + i), j - i, pipecmd, &sk[i]), inputs[i]);
+            printf("%d/%d decomposing %s\r", j, n_in, inputs[j - 1]);
+            i = j;
         }
-        printf("%d/%d decomposing %s\r", i + 1, n_in, inputs[i]);
     }
     printf("\n");
     /* combco.<c>, combco.<c>.a, combco.index.<c>  (command_dist.c:408-470) */

@@ -112,7 +112,10 @@ int mk_fastq_koc_device(mk_ctx *ctx, const void *d_text, size_t nbytes, mk_sketc
 /* h_text: host memory (pinned memory makes the copy asynchronous and faster); the H2D copy
  * is chunked and overlapped with the kernels. */
 int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes, mk_sketch *out);
-/* Same as the reference call: reads `<pipecmd or "zcat -fc"> <path>` through popen(). */
+/* Same as the reference call (iseq2comem.c:664-673): the text of `<pipecmd or "zcat -fc"> <path>`.  Streamed:
+ * line-aligned chunks (MK_INGEST_CHUNK_BYTES, default 64 MB) go through a small ring of pinned buffers, the
+ * copy of chunk i+1 and the read of chunk i+2 run under the sketch of chunk i; host memory does not grow
+ * with the input.  A plain (uncompressed) file is read directly with parallel pread() instead of a pipe. */
 int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out);
 
 /* ---- FASTA genomes (`dist` without -A; MarkerDB-build sketching) ------------------------- */
@@ -121,6 +124,9 @@ int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_ske
 int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_t *offsets, int n_files, mk_sketch *out);
 int mk_fasta_co_host(mk_ctx *ctx, const void *h_text, const uint64_t *offsets, int n_files, mk_sketch *out);
 int mk_fasta_co_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out);
+/* The file loop of run_stageI() (command_dist.c:365, 397-398) as one call: n_files genomes, read by a pool
+ * of threads into a pinned batch buffer and sketched in batches of at most MK_FASTA_BATCH_BYTES (1 GB). */
+int mk_fasta_co_files(mk_ctx *ctx, const char *const *paths, int n_files, const char *pipecmd, mk_sketch *out);
 
 void mk_sketch_free(mk_sketch *s);
 

@@ -83,7 +83,7 @@ class MksParams(C.Structure):  # include/mkssd_synth.h
 EXPORTS = [
     "mk_strerror", "mk_last_error", "mk_device_count", "mk_ctx_create", "mk_ctx_destroy", "mk_ctx_info",
     "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
-    "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_sketch_free", "mk_composite_begin",
+    "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_fasta_co_files", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
     "mk_composite_component_resident", "mk_composite_component_last", "mk_format_species_coverage",
     "mk_fastq_partial_device", "mk_fastq_partial_host",
@@ -124,6 +124,7 @@ def load():
     L.mk_fasta_co_device.argtypes = [vp, vp, vp, i32, C.POINTER(MkSketch)]
     L.mk_fasta_co_host.argtypes = [vp, vp, vp, i32, C.POINTER(MkSketch)]
     L.mk_fasta_co_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(MkSketch)]
+    L.mk_fasta_co_files.argtypes = [vp, vp, i32, C.c_char_p, C.POINTER(MkSketch)]
     L.mk_sketch_free.argtypes = [C.POINTER(MkSketch)]
     L.mk_sketch_free.restype = None
     L.mk_composite_begin.argtypes = [vp, i32]
@@ -342,6 +343,15 @@ class Sketcher:
         n = len(arrs)
         arr = (MkSketch * n)()
         self._ck(self._L.mk_fasta_co_host(self._h, buf.ctypes.data, off.ctypes.data, n, arr))
+        return [_take_sketch(arr[i], False) for i in range(n)]
+
+    def fasta_co_files(self, paths, pipecmd: str = "") -> list:
+        """The FASTA file loop of run_stageI() as one batched call (mk_fasta_co_files)."""
+        n = len(paths)
+        enc = [p.encode() for p in paths]
+        carr = (C.c_char_p * n)(*enc)
+        arr = (MkSketch * n)()
+        self._ck(self._L.mk_fasta_co_files(self._h, carr, n, pipecmd.encode(), arr))
         return [_take_sketch(arr[i], False) for i in range(n)]
 
     def fasta_co_file(self, path: str, pipecmd: str = "") -> Sketch:

@@ -31,7 +31,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(HERE, "build", os.path.basename(src) + ".o")
         objs.append(obj)
         cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-               "-Xcompiler", "-fPIC,-Wno-format-truncation", "-I" + os.path.join(ROOT, "include"), "-c", src, "-o", obj]
+               "-Xcompiler", "-fPIC,-Wno-format-truncation,-pthread", "-I" + os.path.join(ROOT, "include"), "-c", src, "-o", obj]
         cmd += os.environ.get("MK_NVCC_FLAGS", "").split()
         if verbose:
             cmd += ["-Xptxas", "-v"]
@@ -47,7 +47,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if failed:
         raise RuntimeError("nvcc compilation failed")
     # gcc-13 wrapper in this image needs the system g++ for linking
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs + ["-lcudart", "-lpthread"]
     subprocess.run(cmd, check=True)
     return LIB
 

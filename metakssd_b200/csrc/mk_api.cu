@@ -304,43 +304,6 @@ extern "C" int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes,
     return rc;
 }
 
-// popen("<pipecmd or zcat -fc> <path>") like iseq2comem.c:664-669, whole stream into host memory
-static int slurp_pipe(mk_ctx *ctx, const char *path, const char *pipecmd, std::vector<uint8_t> &buf)
-{
-    char cmd[1024];
-    if (pipecmd && pipecmd[0]) snprintf(cmd, sizeof(cmd), "%s %s", pipecmd, path);
-    else snprintf(cmd, sizeof(cmd), "zcat -fc %s", path);
-    FILE *fp = popen(cmd, "r");
-    if (!fp) {
-        snprintf(ctx->err, sizeof(ctx->err), "popen(%s): %s", cmd, strerror(errno));
-        return MK_ERR_IO;
-    }
-    buf.clear();
-    size_t cap = (size_t)64 << 20, n = 0;
-    buf.resize(cap);
-    for (;;) {
-        if (n == cap) { cap *= 2; buf.resize(cap); }
-        size_t got = fread(buf.data() + n, 1, cap - n, fp);
-        if (got == 0) break;
-        n += got;
-    }
-    int st = pclose(fp);
-    buf.resize(n);
-    if (st != 0 && n == 0) {
-        snprintf(ctx->err, sizeof(ctx->err), "%s: exit status %d and no data", cmd, st);
-        return MK_ERR_IO;
-    }
-    return MK_OK;
-}
-
-extern "C" int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out)
-{
-    if (!ctx || !path || !out) return MK_ERR_ARG;
-    std::vector<uint8_t> buf;
-    CKR(slurp_pipe(ctx, path, pipecmd, buf));
-    return mk_fastq_koc_host(ctx, buf.data(), buf.size(), out);
-}
-
 // ---- FASTA ----------------------------------------------------------------------------------------
 extern "C" int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_t *offsets, int n_files, mk_sketch *out)
 {
@@ -377,15 +340,6 @@ extern "C" int mk_fasta_co_host(mk_ctx *ctx, const void *h_text, const uint64_t 
     uint8_t *d = nullptr;
     CKR(upload_text(ctx, h_text, (size_t)offsets[n_files], &d));
     return mk_fasta_co_device(ctx, d, offsets, n_files, out);
-}
-
-extern "C" int mk_fasta_co_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out)
-{
-    if (!ctx || !path || !out) return MK_ERR_ARG;
-    std::vector<uint8_t> buf;
-    CKR(slurp_pipe(ctx, path, pipecmd, buf));
-    uint64_t off[2] = {0, (uint64_t)buf.size()};
-    return mk_fasta_co_host(ctx, buf.data(), off, 1, out);
 }
 
 // development aid (not part of the public header): device buffer of 64 * warps * 8 u64 receiving

@@ -93,6 +93,7 @@ struct mk_ctx {
     const uint8_t *h_src_all = nullptr;   // same pointer; plain upload if the pipelined path is not taken
     std::vector<cudaEvent_t> chunk_ev;
     u64 h_maxpos = 0;                     // read-back slot of mk_runs_finalize_device
+    u64 last_newlines = 0;                // line_base + newlines of the shard mk_fastq_partial_device saw last
     // device copy of the last single-file -A sketch (codes / counts in on-disk order, component bounds)
     const u32 *last_out_code = nullptr;
     const uint16_t *last_out_cnt = nullptr;

@@ -496,6 +496,7 @@ extern "C" int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t n
     CK(cudaSetDevice(ctx->device));
     u64 *cc = nullptr, *cp = nullptr, n_cand = 0, nl = 0;
     CKR(mk_stream_fastq(ctx, (const uint8_t *)d_text, nbytes, pos_base, line_base, false, &cc, &cp, &n_cand, &nl));
+    ctx->last_newlines = nl;
     long long keep_below = LLONG_MAX;
     if (is_last && nbytes) {
         CKR(mk_tail_cut(ctx, (const uint8_t *)d_text, nbytes, &keep_below));

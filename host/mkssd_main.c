@@ -38,6 +38,22 @@ typedef struct {           /* co_dstat_t, global_basic.h:116-126 */
     unsigned long long all_ctx_ct;
 } co_dstat_t;
 
+/* MK_TIMING=1: wall clock of the host program's phases on stderr (development aid) */
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static double g_t0;
+static void phase(const char *what)
+{
+    if (!getenv("MK_TIMING")) return;
+    double t = now_s();
+    fprintf(stderr, "[host timing] %-28s %8.1f ms\n", what, (t - g_t0) * 1e3);
+    g_t0 = t;
+}
+
 static void die(const char *what, const char *arg)
 {
     fprintf(stderr, "metakssd-b200: %s%s%s\n", what, arg ? ": " : "", arg ? arg : "");
@@ -127,12 +143,15 @@ static int cmd_dist(int argc, char **argv)
     if (!shuf) die("-L <file.shuf> is required", NULL);
     if (!n_in) die("no input sequence files", NULL);
     size_t sb;
+    g_t0 = now_s();
     int *sh = slurp(shuf, &sb);
     int shuf_id = sh[0], k = sh[1], subk = sh[2], drl = sh[3];
     if (sb != 16 + ((size_t)4 << (4 * subk))) die("malformed .shuf file", shuf);
+    phase("read .shuf");
 
     mk_ctx *ctx = NULL;
     ck(NULL, mk_ctx_create(&ctx, sh + 4, k, subk, drl, 0), "mk_ctx_create");
+    phase("mk_ctx_create");
     mk_info info;
     mk_ctx_info(ctx, &info);
     printf("rand_id=%d\thalf_ctx_len=%d\thashsize=%u\thashlimit=%u\n", shuf_id, k, info.hashsize, info.hashlimit);
@@ -163,6 +182,7 @@ static int cmd_dist(int argc, char **argv)
         }
     }
     printf("\n");
+    phase("sketching");
     /* combco.<c>, combco.<c>.a, combco.index.<c>  (command_dist.c:408-470) */
     unsigned long long all_ct = 0;
     char path[PATHLEN * 2];
@@ -207,9 +227,11 @@ static int cmd_dist(int argc, char **argv)
         fwrite(name, PATHLEN, 1, fs);
     }
     fclose(fs);
+    phase("write sketch directory");
     for (int i = 0; i < n_in; i++) mk_sketch_free(&sk[i]);
     mk_ctx_destroy(ctx);
     free(sk); free(sh); free(inputs);
+    phase("mk_ctx_destroy");
     return 0;
 }
 
@@ -243,19 +265,17 @@ static int cmd_composite(int argc, char **argv)
         else die("option not on the hot path", argv[i]);
     }
     if (!refdir || !qrydir || !strcmp(refdir, qrydir)) die("refdir or qrydir is not initialized", NULL);
+    g_t0 = now_s();
     sketch_dir R = read_stat(refdir), Q = read_stat(qrydir);
     if (!Q.st.koc) die("get_species_abundance(): query has not abundance", NULL);
     if (Q.st.shuf_id != R.st.shuf_id)
         printf("get_species_abundance(): qry shuf_id %u not match ref shuf_id: %u\n", Q.st.shuf_id, R.st.shuf_id);
-    /* the library needs the sketch geometry only for its context; composite itself is geometry free */
+    /* composite is geometry free: a context without pass-set tables */
     int k = R.st.kmerlen / 2, drl = R.st.dim_rd_len / 2;
     int subk = drl + 3 > k ? k : drl + 3;
-    size_t np = (size_t)1 << (4 * subk);
-    int32_t *perm = malloc(np * 4);
-    for (size_t i = 0; i < np; i++) perm[i] = (int32_t)i;
     mk_ctx *ctx = NULL;
-    ck(NULL, mk_ctx_create(&ctx, perm, k, subk, drl, 0), "mk_ctx_create");
-    free(perm);
+    ck(NULL, mk_ctx_create(&ctx, NULL, k, subk, drl, 0), "mk_ctx_create");
+    phase("mk_ctx_create");
     int S = R.st.infile_num;
     mk_species_stat *stats = malloc(sizeof *stats * (size_t)S);
     int *order = malloc(sizeof(int) * (size_t)S);
@@ -288,7 +308,9 @@ static int cmd_composite(int argc, char **argv)
                    (float)s->lastsum / s->lastn, s->median, s->max);    /* command_composite.c:624 */
         }
     }
+    phase("composite");
     mk_ctx_destroy(ctx);
+    phase("mk_ctx_destroy");
     return 0;
 }
 

@@ -95,7 +95,8 @@ const char *mk_strerror(int code);
 const char *mk_last_error(const mk_ctx *ctx);
 int mk_device_count(void);
 
-/* shuf_perm: the 16^subk int32 permutation of the .shuf file (host memory). */
+/* shuf_perm: the 16^subk int32 permutation of the .shuf file (host memory).  NULL creates a context without
+ * pass-set tables, good for the composite entry points only (sketching calls then return MK_ERR_ARG). */
 int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int subk, int drlevel, int device);
 void mk_ctx_destroy(mk_ctx *ctx);
 int mk_ctx_info(const mk_ctx *ctx, mk_info *info);

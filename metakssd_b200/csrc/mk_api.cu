@@ -56,7 +56,7 @@ static u64 pair_reverse(u64 v, int pairs)
 
 extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int subk, int drlevel, int device)
 {
-    if (!out || !shuf_perm) return MK_ERR_ARG;
+    if (!out) return MK_ERR_ARG;
     *out = nullptr;
     if (k < 2 || k > 16 || subk < 1 || subk > 7 || subk > k || drlevel < 0 || drlevel > subk) return MK_ERR_PARAM;
     int primer_ind = 4 * (k - drlevel) - 8 - 7; // CTX_SPC_USE_L = 8
@@ -121,6 +121,11 @@ extern "C" int mk_ctx_create(mk_ctx **out, const int32_t *shuf_perm, int k, int 
     if (K.prew > 2) return fail(MK_ERR_UNSUPPORTED);
     K.shift_s = 2 * (16 * K.prew - K.pre - K.spare);
 
+    if (!shuf_perm) {          // composite-only context: no pass-set tables (sketching calls return MK_ERR_ARG)
+        ctx->no_tables = true;
+        *out = ctx;
+        return MK_OK;
+    }
     // pass set -> exact table (dim -> pf) and the probe bitmap over S ∪ revcomp(S)
     const u64 ndim = 1ull << (4 * subk);
     const u64 mwmask = ndim - 1;

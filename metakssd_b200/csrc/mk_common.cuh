@@ -75,6 +75,7 @@ struct mk_ctx {
     u32 *d_bitmap3 = nullptr;       // two-plane core filter of k_stream3 (mk_stream3.cu)
     u32 bitmap3_words = 0;
     u64 *d_ptab = nullptr;
+    bool no_tables = false;         // context created without a permutation (composite only)
     void *d_trace = nullptr;        // development aid: phase timestamps of CTA 0 (mk_debug_set_trace)
     Scratch sb[SB_NUM];
     void *h_pinned = nullptr;       // small pinned staging block

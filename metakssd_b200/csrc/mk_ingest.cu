@@ -171,6 +171,12 @@ struct Chunk {
     int rc = MK_OK;
 };
 
+int default_threads()
+{
+    unsigned n = std::thread::hardware_concurrency();
+    return n == 0 ? 8 : (n > 32 ? 32 : (int)n);
+}
+
 int env_int(const char *name, int dflt, int lo, int hi)
 {
     const char *e = getenv(name);
@@ -197,7 +203,7 @@ extern "C" int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipe
         if (chunk < 2 * (MK_LINE_MAX + 1)) chunk = 2 * (MK_LINE_MAX + 1);
         chunk = (chunk + 4095) & ~(size_t)4095;
         const int NB = env_int("MK_INGEST_BUFFERS", 4, 3, 16);
-        const int threads = env_int("MK_INGEST_THREADS", 8, 1, 64);
+        const int threads = env_int("MK_INGEST_THREADS", default_threads(), 1, 64);
         const size_t cap = chunk + 2 * (MK_LINE_MAX + 1) + 256;        // + a carried partial line + the final one
 
         std::vector<Pinned> hbuf((size_t)NB);
@@ -423,7 +429,7 @@ extern "C" int mk_fasta_co_files(mk_ctx *ctx, const char *const *paths, int n_fi
         size_t batch = (size_t)1 << 30;
         if (const char *e = getenv("MK_FASTA_BATCH_BYTES")) batch = (size_t)atoll(e);
         if (batch < (1u << 20)) batch = 1u << 20;
-        const int threads = env_int("MK_INGEST_THREADS", 8, 1, 64);
+        const int threads = env_int("MK_INGEST_THREADS", default_threads(), 1, 64);
         Pinned buf;
         CKR(buf.alloc(ctx, batch + 256));
         std::vector<uint8_t> tmp;

@@ -72,7 +72,9 @@ k_acc_insert(const u64 *__restrict__ cand_code, const u64 *__restrict__ cand_pos
         h = (h + 1) & mask;
     }
     u32 add = cand_cnt ? cand_cnt[i] : 1u;
-    atomicAdd(&cnt[h], add);
+    // counts saturate (the output clamps at 65535, iseq2comem.c:713): once a slot passes 2^31 it is pinned there
+    // instead of wrapping after 2^32 occurrences of one code
+    if (atomicAdd(&cnt[h], add) > 0x7FFFFFFFu) atomicExch(&cnt[h], 0x80000000u);
     atomicMin((unsigned long long *)&minpos[h], pos);
 }
 
@@ -124,7 +126,7 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
     // Reads repeat their k-mers many times over: start with a table a quarter of the candidate count
     // (clearing and compacting the table is what this step costs) and fall back to 2n slots if a probe
     // sequence gets long.  Genome batches (file_off) are mostly distinct codes: full size at once.
-    const u64 cap_full = pow2_at_least(2 * n + 2);
+    u64 cap_full = pow2_at_least(2 * n + 2);
     u64 cap = (d_file_off || d_cnt) ? cap_full : pow2_at_least(n / 4 + 2);   // (runs being merged are mostly distinct too)
     if (cap < (1ull << 16)) cap = cap_full < (1ull << 16) ? cap_full : (1ull << 16);
     if (cap > cap_full) cap = cap_full;
@@ -157,8 +159,14 @@ static int accumulate(mk_ctx *ctx, const u64 *d_code, const u64 *d_pos, const u3
     CK(cudaMemcpyAsync(h2, counters + 4, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->prof.d2h_bytes += 16;
-    if (h2[1] && cap < cap_full) {        // a probe sequence ran long: once more with the full-size table
-        cap = cap_full;
+    if (h2[1]) {        // a probe sequence ran past its limit: a candidate was dropped, the result is not usable
+        if (cap < cap_full) cap = cap_full;                  // once more with the full-size table
+        else if (cap_full < (16 * n + 1024)) cap = cap_full = cap_full * 2;   // (clustered keys: a sparser table)
+        else {
+            snprintf(ctx->err, sizeof(ctx->err), "count accumulation: probe limit reached with a table of %llu slots for %llu candidates",
+                     (unsigned long long)cap, (unsigned long long)n);
+            return MK_ERR_NOMEM;
+        }
         goto retry;
     }
     *n_items = h2[0];

@@ -1373,6 +1373,10 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
 {
     *n_cand = 0;
     if (n_newlines) *n_newlines = line_base;
+    if (ctx->no_tables) {
+        snprintf(ctx->err, sizeof(ctx->err), "this context was created without a .shuf permutation (composite only)");
+        return MK_ERR_ARG;
+    }
     if (nbytes == 0) return MK_OK;
     if ((uintptr_t)d_text & 15) {
         snprintf(ctx->err, sizeof(ctx->err), "device text pointer must be 16-byte aligned");

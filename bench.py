@@ -292,9 +292,27 @@ def run_ours(args):
 
     # `value` leg: everything the step reads is resident in HBM (FASTQ text and MarkerDB);
     # `e2e` leg: host buffers, the MarkerDB is uploaded with every step like the reference re-reads it
-    if rank == 0:
+    use_lib_comm = world > 1 and os.environ.get("MK_DIST", "nccl-lib") != "torch"
+    if use_lib_comm:       # exchange, owner merge and rank-local composite inside the library (csrc/mk_comm.cu)
+        D.init_library_comm(sk)
+        sk.load_markerdb_sharded(mdb.comp)
+    elif rank == 0:
         sk.load_markerdb(mdb.comp)
     names_c = M.SpeciesNames(mdb.names)
+    max_runs = 0
+    if use_lib_comm:       # block capacity of the exchange: the runs of the fullest shard, with headroom
+        n_local = int(sk.fastq_partial_device(d_text, nbytes, pos_base, 4 * r0, rank == world - 1).n)
+        t = torch.tensor([n_local], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        max_runs = int(t.item()) * 5 // 4 + 4096
+
+    def sharded_step(text, nb, pb, lb, last, host_text=False):
+        """(sketch, tsv) on rank 0, (None, None) elsewhere"""
+        if use_lib_comm:
+            s_, st = sk.fastq_koc_sharded(text, nb, pb, lb, last, max_runs, host_text=host_text)
+            return (s_, M.coverage_tsv("reads.fq", names_c, st)) if rank == 0 else (None, None)
+        s_ = D.sketch_sharded(sk, text, nb, pb, lb, last, host_text=host_text)
+        return (s_, composite(s_, not host_text)) if rank == 0 else (None, None)
 
     def composite(sketch, resident):
         if resident:        # MarkerDB and the sketch just produced are both on the device
@@ -322,7 +340,7 @@ def run_ours(args):
             n_sh = min(200_000, per_rank)
             nb_sh = spec.fastq_bytes(r0, r0 + n_sh)
             sizes = [spec.fastq_bytes(q * per_rank, q * per_rank + n_sh) for q in range(world)]
-            s_sh = D.sketch_sharded(sk, d_text, nb_sh, sum(sizes[:rank]), 4 * n_sh * rank, rank == world - 1)
+            s_sh, tsv_sh = sharded_step(d_text, nb_sh, sum(sizes[:rank]), 4 * n_sh * rank, rank == world - 1)
             if rank == 0:
                 cat = torch.empty(sum(sizes) + 256, dtype=torch.uint8, device=dev)
                 o = 0
@@ -331,8 +349,16 @@ def run_ours(args):
                     o += sizes[q]
                 single = sk.fastq_koc_device(cat, sum(sizes))
                 del cat
-                parity["sharded_vs_single"] = {"ok": _same_sketch(s_sh, single), "records_per_rank": n_sh, "ranks": world,
-                                               "codes": int(single.n_total)}
+                if use_lib_comm:      # the single-GPU composite needs the whole MarkerDB: a second context holds it
+                    with M.Sketcher(perm, K, SUBK, L, device=local) as sk1:
+                        qry = [(single.codes[c], single.counts[c]) for c in range(len(single.codes))]
+                        tsv_single = M.coverage_tsv("reads.fq", names_c, sk1.composite(mdb.comp, qry))
+                else:
+                    tsv_single = composite(single, False)
+                parity["sharded_vs_single"] = {"ok": _same_sketch(s_sh, single) and tsv_sh == tsv_single,
+                                               "records_per_rank": n_sh, "ranks": world, "codes": int(single.n_total),
+                                               "coverage_rows": tsv_single.count("\n"),
+                                               "path": "library NCCL exchange + rank-local composite" if use_lib_comm else "torch.distributed all-to-all"}
             flag = torch.tensor([1 if rank != 0 or parity["sharded_vs_single"]["ok"] else 0], device=dev)
             dist.broadcast(flag, 0)                 # every rank leaves together on a mismatch
             if int(flag.item()) == 0:
@@ -341,8 +367,7 @@ def run_ours(args):
     def step_device():
         if world == 1:
             return composite(sk.fastq_koc_device(d_text, nbytes), True)
-        s = D.sketch_sharded(sk, d_text, nbytes, pos_base, 4 * r0, rank == world - 1)
-        return composite(s, True) if rank == 0 else None
+        return sharded_step(d_text, nbytes, pos_base, 4 * r0, rank == world - 1)[1]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -394,8 +419,7 @@ def run_ours(args):
                 return composite(sk.fastq_koc_host(h_text), False)
             # multi-GPU: every rank uploads its shard from its own pinned buffer (chunks overlapped with
             # the kernel), then the sharded path
-            s = D.sketch_sharded(sk, h_text, e_nbytes, pos_base, 4 * r0, rank == world - 1, host_text=True)
-            return composite(s, False) if rank == 0 else None
+            return sharded_step(h_text, e_nbytes, pos_base, 4 * r0, rank == world - 1, host_text=True)[1]
 
         e_steps = max(2, min(args.steps, 3))
         timed(step_host, 0, 1)
@@ -448,12 +472,14 @@ def run_ours(args):
         "config": {"workload": workload_name(args, world), "config": args.config, "k": K, "subk": SUBK, "L": L,
                    "reads_per_gpu": per_rank, "read_len": READ_LEN, "species": args.species, "genome_len": args.genome_len,
                    "markerdb_codes": mdb.n_codes, "l2_policy": "input (%.1f GB per GPU) is far larger than L2" % (nbytes / 1e9),
-                   "parallelism": "reads sharded per GPU, runs exchanged by code range (all-to-all)" if world > 1 else "1 GPU",
+                   "parallelism": ("reads sharded per GPU; runs exchanged by code range in one grouped ncclSend/ncclRecv step inside the "
+                                   "library, MarkerDB sharded on the same boundaries (rank-local composite), slot order on rank 0"
+                                   if use_lib_comm else "reads sharded per GPU, runs exchanged by code range (torch all-to-all)") if world > 1 else "1 GPU",
                    "markerdb_build_s": t_mdb, "species_reported": tsv.count("\n") if tsv else 0},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "cli_e2e": cli, "parity": parity,
         "gpu_launches": int(prof.kernel_launches), "clocks": clocks,
         "breakdown_ms_per_step": {"stream_kernel": prof.stream_kernel_ms / args.steps, "reduce_order": prof.reduce_ms / args.steps,
-                                  "composite": prof.composite_ms / args.steps},
+                                  "composite": prof.composite_ms / args.steps, "exchange": prof.exchange_ms / args.steps},
     }
     print(json.dumps(line))
     if world > 1:

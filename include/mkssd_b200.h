@@ -89,6 +89,7 @@ typedef struct mk_profile {
     double composite_ms;
     uint64_t kernel_launches;    /* every kernel launched by this context                   */
     uint64_t h2d_bytes, d2h_bytes;
+    double exchange_ms;          /* multi-GPU: pack + NCCL exchange + owner merge + rank-local composite + gather */
 } mk_profile;
 
 const char *mk_strerror(int code);
@@ -205,6 +206,28 @@ int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_
                          uint64_t n, mk_runs *merged);
 /* number of '\n' bytes in a device buffer (to derive line_base of the next shard) */
 int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t *count);
+
+/* ---- the multi-GPU step inside the library (NCCL over NVLink; one context per rank / GPU) -------- */
+/* mk_comm_unique_id(): 128 bytes from ncclGetUniqueId() on one rank, handed to all ranks by the host's own
+ * means (MPI / torch.distributed / a file); mk_comm_init() joins the communicator (ncclCommInitRank).  NCCL is
+ * loaded with dlopen("libnccl.so.2") on first use. */
+int mk_comm_unique_id(void *id, size_t bytes);
+int mk_comm_init(mk_ctx *ctx, const void *id, int rank, int world);
+int mk_comm_destroy(mk_ctx *ctx);
+/* This rank's slice of a MarkerDB component: the codes whose full code falls into its code range (the same
+ * boundaries the runs are exchanged on), kept resident; also records every rank's slice size.  Every rank calls
+ * it with the WHOLE component. */
+int mk_markerdb_load_sharded(mk_ctx *ctx, int component, const uint32_t *ref_codes, const uint64_t *ref_index,
+                             int n_species);
+/* The whole sharded step for this rank's shard of the FASTQ text (collective: every rank calls it).  Runs go to
+ * the owner of their code range in one grouped ncclSend/ncclRecv step (blocks of `max_runs` slots per pair, count
+ * in a header; MK_ERR_NOMEM if a block overflows), owners merge, probe their MarkerDB slice (if one is loaded)
+ * and send hits and merged runs to rank 0.  On rank 0: `out` = the sketch of the whole file in reference order,
+ * `stats` (may be NULL) = per-species statistics; other ranks pass NULL / get nothing. */
+int mk_fastq_koc_sharded_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,
+                                int is_last, uint64_t max_runs, mk_sketch *out, mk_species_stat *stats);
+int mk_fastq_koc_sharded_host(mk_ctx *ctx, const void *h_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,
+                              int is_last, uint64_t max_runs, mk_sketch *out, mk_species_stat *stats);
 
 /* ---- synthetic workload generator on the device (bench / tests; mkssd_synth.h) ----------- */
 struct mks_params;

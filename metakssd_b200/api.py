@@ -59,6 +59,7 @@ class MkProfile(C.Structure):
         ("stream_kernel_ms", C.c_double), ("stream_kernel_launches", C.c_uint64),
         ("stream_kernel_bytes", C.c_uint64), ("reduce_ms", C.c_double), ("composite_ms", C.c_double),
         ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+        ("exchange_ms", C.c_double),
     ]
 
 
@@ -90,6 +91,8 @@ EXPORTS = [
     "mk_runs_finalize_device", "mk_runs_finalize_distinct_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
+    "mk_comm_unique_id", "mk_comm_init", "mk_comm_destroy", "mk_markerdb_load_sharded", "mk_fastq_koc_sharded_device",
+    "mk_fastq_koc_sharded_host",
 ]
 
 _lib = None
@@ -157,6 +160,12 @@ def load():
     L.mk_synth_shuf_perm.restype = None
     L.mk_synth_shuf_id.argtypes = [u64]
     L.mk_synth_shuf_id.restype = C.c_int32
+    L.mk_comm_unique_id.argtypes = [vp, sz]
+    L.mk_comm_init.argtypes = [vp, vp, i32, i32]
+    L.mk_comm_destroy.argtypes = [vp]
+    L.mk_markerdb_load_sharded.argtypes = [vp, i32, vp, vp, i32]
+    L.mk_fastq_koc_sharded_device.argtypes = [vp, vp, sz, u64, u64, i32, u64, C.POINTER(MkSketch), vp]
+    L.mk_fastq_koc_sharded_host.argtypes = [vp, vp, sz, u64, u64, i32, u64, C.POINTER(MkSketch), vp]
     _lib = L
     return L
 
@@ -439,6 +448,42 @@ class Sketcher:
         r = MkRuns()
         self._ck(self._L.mk_runs_merge_device(self._h, _ptr(d_code), _ptr(d_pos), _ptr(d_cnt), n, C.byref(r)))
         return r
+
+    # -- the multi-GPU step inside the library (NCCL; csrc/mk_comm.cu)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = load().mk_comm_unique_id(buf, 128)
+        if rc != MK_OK:
+            raise MkError(rc, load().mk_strerror(rc).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        self._ck(self._L.mk_comm_init(self._h, C.c_char_p(unique_id), rank, world))
+        self.rank, self.world = rank, world
+
+    def load_markerdb_sharded(self, ref_comp):
+        """Every rank passes the WHOLE MarkerDB; the library keeps this rank's code-range slice resident."""
+        self._ck(self._L.mk_markerdb_unload(self._h))
+        self._mdb_species = int(ref_comp[0][1].size - 1)
+        self._mdb_components = len(ref_comp)
+        for c, (rc, ri) in enumerate(ref_comp):
+            rc = np.ascontiguousarray(rc, dtype=np.uint32)
+            ri = np.ascontiguousarray(ri, dtype=np.uint64)
+            self._ck(self._L.mk_markerdb_load_sharded(self._h, c, rc.ctypes.data, ri.ctypes.data, self._mdb_species))
+
+    def fastq_koc_sharded(self, text, nbytes: int, pos_base: int, line_base: int, is_last: bool, max_runs: int,
+                          host_text: bool = False, want_stats: bool = True):
+        """Collective.  Returns (Sketch, stats) on rank 0 and (None, None) elsewhere."""
+        sk = MkSketch()
+        root = getattr(self, "rank", 0) == 0
+        stats = np.zeros(getattr(self, "_mdb_species", 0), dtype=STATS_DTYPE) if (root and want_stats and getattr(self, "_mdb_species", 0)) else None
+        fn = self._L.mk_fastq_koc_sharded_host if host_text else self._L.mk_fastq_koc_sharded_device
+        self._ck(fn(self._h, _ptr(text), nbytes, pos_base, line_base, 1 if is_last else 0, max_runs,
+                    C.byref(sk) if root else None, stats.ctypes.data if stats is not None else None))
+        if not root:
+            return None, None
+        return _take_sketch(sk, True), stats
 
     def count_newlines_device(self, d_text, nbytes: int) -> int:
         v = C.c_uint64()

@@ -198,6 +198,7 @@ extern "C" void mk_ctx_destroy(mk_ctx *ctx)
     if (ctx->d_bitmap3) cudaFree(ctx->d_bitmap3);
     if (ctx->d_ptab) cudaFree(ctx->d_ptab);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    mk_comm_destroy(ctx);
     mk_markerdb_unload(ctx);
     for (cudaEvent_t e : ctx->chunk_ev) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -51,7 +51,8 @@ enum {
     SB_OUT_KEY, SB_SEG_COUNTS, SB_TEXT, SB_SCAN_TMP, SB_FA_STATE, SB_FA_CNT, SB_FA_DENSE, SB_FA_OFF,
     SB_CQ_KEYS, SB_CQ_IDX, SB_C_REF, SB_C_IDX, SB_C_QRY, SB_C_QCNT, SB_C_HITVAL, SB_C_POS, SB_C_STORE_S,
     SB_C_STORE_C, SB_C_STATS, SB_C_NH, SB_SYN_CDF, SB_SYN_SPC, SB_MISC, SB_FILE_OFF, SB_RUN_CODE,
-    SB_RUN_POS, SB_RUN_CNT, SB_TILE_DESC8, SB_S3_ARENA, SB_NUM
+    SB_RUN_POS, SB_RUN_CNT, SB_TILE_DESC8, SB_S3_ARENA, SB_X_CUT, SB_X_SHDR, SB_X_SCODE, SB_X_SPOS, SB_X_SCNT,
+    SB_X_RCODE, SB_X_RPOS, SB_X_RCNT, SB_X_QCODE, SB_X_QCNT, SB_X_QN, SB_X_HITS, SB_NUM
 };
 
 struct ResidentComponent {         // one MarkerDB component kept on the device (mk_markerdb_load)
@@ -89,6 +90,10 @@ struct mk_ctx {
     std::vector<int32_t> comp_lists_flat;
     std::vector<const int32_t *> comp_lists_ptr;
     std::vector<ResidentComponent> mdb;
+    // multi-GPU (mk_comm.cu): NCCL communicator, this rank, and per component the MarkerDB slice size of every rank
+    void *comm = nullptr;
+    int rank = 0, world = 1;
+    std::vector<std::vector<u64>> mdb_shard_sizes;
     // host text handed from mk_fastq_koc_host to the stream driver (uploaded there, chunk by chunk)
     const uint8_t *h_src = nullptr;       // pipelined upload (pinned or pageable)
     const uint8_t *h_src_all = nullptr;   // same pointer; plain upload if the pipelined path is not taken
@@ -208,6 +213,8 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
                       bool with_counts, bool drop_zero_code, mk_sketch *out);
 int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_base, u64 line_base, bool raw_mode,
                     u64 **d_cand_code, u64 **d_cand_pos, u64 *n_cand, u64 *n_newlines);
+int mk_composite_reserve(mk_ctx *ctx, u64 extra);
+int mk_composite_component_dev(mk_ctx *ctx, int component, const u32 *d_qry, const uint16_t *d_qcnt, u64 q);
 int mk_tail_cut(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, long long *keep_below);
 int mk_fasta_compact(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, const u64 *h_offsets, int n_files,
                      uint8_t **d_dense, u64 *dense_bytes, u64 **d_dense_off);

@@ -79,12 +79,35 @@ extern "C" int mk_composite_begin(mk_ctx *ctx, int n_species)
     return MK_OK;
 }
 
+// room for `extra` more hits in the per-context store, keeping its content
+int mk_composite_reserve(mk_ctx *ctx, u64 extra)
+{
+    u64 need = ctx->comp_nhits + extra;
+    Scratch &ss = ctx->sb[SB_C_STORE_S], &sc = ctx->sb[SB_C_STORE_C];
+    if (ss.bytes < need * 4 || sc.bytes < need * 4) {
+        u32 *ns, *nc;
+        size_t bytes = (size_t)(need + need / 2) * 4 + 256;
+        CK(cudaMalloc(&ns, bytes));
+        CK(cudaMalloc(&nc, bytes));
+        if (ctx->comp_nhits) {
+            CK(cudaMemcpyAsync(ns, ss.p, ctx->comp_nhits * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(nc, sc.p, ctx->comp_nhits * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        if (ss.p) cudaFree(ss.p);
+        if (sc.p) cudaFree(sc.p);
+        ss.p = ns; ss.bytes = bytes;
+        sc.p = nc; sc.bytes = bytes;
+    }
+    return MK_OK;
+}
+
 // One MarkerDB component against the query codes [qry_lo, qry_hi).  The MarkerDB side is either the
 // host arrays of the call (uploaded now) or a component made resident by mk_markerdb_load().
 static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, const u32 *res_ref,
                                const u64 *res_index, u64 r, int n_species, const uint32_t *qry_codes,
                                const uint16_t *qry_counts, uint64_t qry_lo, uint64_t qry_hi,
-                               const u32 *dev_qry = nullptr, const uint16_t *dev_qcnt = nullptr)
+                               const u32 *dev_qry = nullptr, const uint16_t *dev_qcnt = nullptr, bool slice = false)
 {
     CK(cudaSetDevice(ctx->device));
     const u64 q = qry_hi - qry_lo;
@@ -92,7 +115,7 @@ static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uin
     // a table of 0 slots: both loops run zero times, the component contributes no hits and the run goes on.
     // q == 1 gives 1 slot and HASH() then takes K % (hash_sz - 1) = K % 0: the reference dies with SIGFPE.
     if (q == 0 || r == 0) return MK_OK;
-    if (q == 1) {
+    if (q == 1 && !slice) {     // (a code-range slice of a sharded query with one code is not the reference's one-code query)
         snprintf(ctx->err, sizeof(ctx->err), "composite: query component with exactly one code (the reference divides by zero)");
         return MK_ERR_EMPTY_QUERY;
     }
@@ -119,27 +142,9 @@ static int composite_component(mk_ctx *ctx, const uint32_t *ref_codes, const uin
     CKR(mk_scratch(ctx, SB_CQ_KEYS, (size_t)cap, &d_keys));
     CKR(mk_scratch(ctx, SB_CQ_IDX, (size_t)cap, &d_idx));
     // grow the hit store, keeping what earlier components appended
-    {
-        u64 need = ctx->comp_nhits + r;
-        Scratch &ss = ctx->sb[SB_C_STORE_S], &sc = ctx->sb[SB_C_STORE_C];
-        if (ss.bytes < need * 4 || sc.bytes < need * 4) {
-            u32 *ns, *nc;
-            size_t bytes = (size_t)(need + need / 2) * 4 + 256;
-            CK(cudaMalloc(&ns, bytes));
-            CK(cudaMalloc(&nc, bytes));
-            if (ctx->comp_nhits) {
-                CK(cudaMemcpyAsync(ns, ss.p, ctx->comp_nhits * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-                CK(cudaMemcpyAsync(nc, sc.p, ctx->comp_nhits * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-                CK(cudaStreamSynchronize(ctx->stream));
-            }
-            if (ss.p) cudaFree(ss.p);
-            if (sc.p) cudaFree(sc.p);
-            ss.p = ns; ss.bytes = bytes;
-            sc.p = nc; sc.bytes = bytes;
-        }
-        store_s = (u32 *)ss.p;
-        store_c = (u32 *)sc.p;
-    }
+    CKR(mk_composite_reserve(ctx, r));
+    store_s = (u32 *)ctx->sb[SB_C_STORE_S].p;
+    store_c = (u32 *)ctx->sb[SB_C_STORE_C].p;
     if (!res_ref) {
         CK(cudaMemcpyAsync(d_ref, ref_codes, (size_t)r * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(d_index, ref_index, (size_t)(n_species + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -240,6 +245,17 @@ extern "C" int mk_composite_component_last(mk_ctx *ctx, int component)
     return composite_component(ctx, nullptr, nullptr, m.d_ref, m.d_index, m.r, m.n_species, nullptr, nullptr,
                                ctx->last_seg[(size_t)component], ctx->last_seg[(size_t)component + 1], ctx->last_out_code,
                                ctx->last_out_cnt);
+}
+
+// resident MarkerDB component against a query that already sits on the device (the merged runs of a code range,
+// mk_comm.cu): the same intersection, no upload
+int mk_composite_component_dev(mk_ctx *ctx, int component, const u32 *d_qry, const uint16_t *d_qcnt, u64 q)
+{
+    if (!ctx || component < 0 || (size_t)component >= ctx->mdb.size()) return MK_ERR_ARG;
+    const ResidentComponent &m = ctx->mdb[(size_t)component];
+    if (!m.d_index || m.n_species != ctx->comp_species) return MK_ERR_ARG;
+    return composite_component(ctx, nullptr, nullptr, m.d_ref, m.d_index, m.r, m.n_species, nullptr, nullptr, 0, q, d_qry,
+                               d_qcnt, true);
 }
 
 // ---- species_coverage lines (host): command_composite.c:582-624 ------------------------------------

@@ -73,6 +73,19 @@ def merge_runs_reference(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tenso
     return uniq, pmin, torch.clamp(ksum, max=65535).to(cnt.dtype)
 
 
+def init_library_comm(sk, group=None):
+    """Join the library's own NCCL communicator (csrc/mk_comm.cu): rank 0 draws the unique id, torch.distributed
+    (any backend) only carries its 128 bytes to the other ranks."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", sk.info.device) if backend == "nccl" else torch.device("cpu")
+    buf = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        buf.copy_(torch.frombuffer(bytearray(sk.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(buf, 0, group=group)
+    sk.comm_init(bytes(buf.cpu().numpy().tobytes()), rank, world)
+
+
 def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_last: bool, group=None,
                    host_text: bool = False):
     """The whole multi-GPU step for this rank's shard.  Returns the final Sketch on rank 0 (None

@@ -1,6 +1,8 @@
-"""GPU (needs >= 2 devices, skipped otherwise): the sharded path — per-rank partial sketches, NCCL
-all-to-all by code range, merge, slot-order reconstruction on rank 0 — must give exactly the sketch
-of the concatenated input on one GPU."""
+"""GPU (needs >= 2 devices, skipped otherwise; `bench.py --gpus N` repeats the same check before it times
+anything): the sharded path — per-rank partial sketches, exchange by code range, owner merge, slot-order
+reconstruction on rank 0 — must give exactly the sketch of the concatenated input on one GPU, through the
+torch.distributed all-to-all of distributed.py AND through the library's own NCCL step (csrc/mk_comm.cu), whose
+rank-local composite against the code-range slices of the MarkerDB must give the single-GPU statistics."""
 import os
 import subprocess
 import sys
@@ -37,6 +39,25 @@ WORKER = textwrap.dedent('''
     os.environ["MK_CHUNK_BYTES"] = "3000000"
     got_h = D.sketch_sharded(sk, h, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, host_text=True)
     del os.environ["MK_CHUNK_BYTES"]
+    # the same step inside the library: grouped ncclSend/ncclRecv by code range, owner merge, rank-local composite
+    # against the MarkerDB slice of the code range, slot order on rank 0 (csrc/mk_comm.cu)
+    from metakssd_b200 import workload as W
+    mdb = W.build_markerdb(sk, spec)
+    D.init_library_comm(sk)
+    sk.load_markerdb_sharded(mdb.comp)
+    n_local = int(sk.fastq_partial_device(d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1).n)
+    t = torch.tensor([n_local], dtype=torch.int64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    cap = int(t.item()) * 5 // 4 + 4096
+    got_l, stats_l = sk.fastq_koc_sharded(d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, cap)
+    got_lh, stats_lh = sk.fastq_koc_sharded(h, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, cap, host_text=True)
+    # a block capacity that is too small must be reported, not silently truncated
+    failed = 0
+    try:
+        sk.fastq_koc_sharded(d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, 64)
+    except M.MkError as e:
+        failed = 1 if e.code == -4 else 0
+    f = torch.tensor([failed], dtype=torch.int64, device=dev); dist.all_reduce(f, op=dist.ReduceOp.MAX)
+    assert int(f.item()) == 1, "an overflowing exchange block went unnoticed"
     if rank == 0:
         nball = spec.fastq_bytes(0, world * per)
         full = torch.empty(nball + 256, dtype=torch.uint8, device=dev)
@@ -48,6 +69,12 @@ WORKER = textwrap.dedent('''
             assert np.array_equal(got.counts[c], want.counts[c]), "counts differ"
             assert np.array_equal(got_h.codes[c], want.codes[c]), "host-text path: codes/order differ"
             assert np.array_equal(got_h.counts[c], want.counts[c]), "host-text path: counts differ"
+            assert np.array_equal(got_l.codes[c], want.codes[c]) and np.array_equal(got_l.counts[c], want.counts[c]), "library path differs"
+            assert np.array_equal(got_lh.codes[c], want.codes[c]) and np.array_equal(got_lh.counts[c], want.counts[c]), "library path (host text) differs"
+        with M.Sketcher(perm, k, subk, L, device=local) as sk1:      # whole MarkerDB, whole sketch, one GPU
+            want_stats = sk1.composite(mdb.comp, [(want.codes[c], want.counts[c]) for c in range(len(want.codes))])
+        assert np.array_equal(stats_l, want_stats) and np.array_equal(stats_lh, want_stats), "sharded composite differs"
+        assert int((want_stats["n"] >= 6).sum()) >= 5
         print("MULTI_OK", want.n_total)
     dist.barrier()
     dist.destroy_process_group()

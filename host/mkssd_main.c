@@ -9,7 +9,8 @@
  *
  *   metakssd-b200 shuffle -k 11 -s 6 -l 3 -o L3K11 [--seed N]
  *   metakssd-b200 dist -L L3K11.shuf -A -o sketch reads.fq [more inputs ...]
- *   metakssd-b200 dist -L L3K11.shuf -o gsk sp1.fasta sp2.fasta ...
+ *   metakssd-b200 dist -L L3K11.shuf -o gsk [-u] sp1.fasta sp2.fasta ...
+ *   metakssd-b200 dist -L L3K11.shuf -o sk [-Q 20] [-n 2] reads.fq        (no -A: fastq2co)
  *   metakssd-b200 composite -r markerdb -q sketch > species_coverage.tsv
  *
  * Differences from the reference, all outside the sketch content: input files keep their command
@@ -128,7 +129,8 @@ static int cmd_shuffle(int argc, char **argv)
 static int cmd_dist(int argc, char **argv)
 {
     const char *shuf = NULL, *outdir = "./", *pipecmd = "";
-    bool abundance = false;
+    bool abundance = false, dedup = false;
+    int kmerqlty = 0, kmerocrs = 1;            /* command_dist_wrapper.c:79-80 */
     char **inputs = malloc(sizeof(char *) * (size_t)(argc + 1));
     int n_in = 0;
     for (int i = 0; i < argc; i++) {
@@ -137,6 +139,14 @@ static int cmd_dist(int argc, char **argv)
         else if (!strcmp(argv[i], "-p") && i + 1 < argc) ++i;
         else if (!strcmp(argv[i], "-P") && i + 1 < argc) pipecmd = argv[++i];
         else if (!strcmp(argv[i], "-A")) abundance = true;
+        else if (!strcmp(argv[i], "-u")) dedup = true;
+        else if (!strcmp(argv[i], "-Q") && i + 1 < argc) kmerqlty = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-n") && i + 1 < argc) {        /* clamped to 1..7 like command_dist_wrapper.c:169-179 */
+            int v = atoi(argv[++i]);
+            if (v > 7) { fprintf(stderr, "metakssd-b200: -n argument is larger than Max, it has been set to 7, ignorned -n %d \n", v); v = 7; }
+            if (v < 1) { fprintf(stderr, "metakssd-b200: -n argument is smaller than Min, it has been set to 1, ignorned -n %d \n", v); v = 1; }
+            kmerocrs = v;
+        }
         else if (argv[i][0] == '-') die("option not on the hot path", argv[i]);
         else inputs[n_in++] = argv[i];
     }
@@ -166,13 +176,16 @@ static int cmd_dist(int argc, char **argv)
             ck(ctx, mk_fastq_koc_file(ctx, inputs[i], pipecmd, &sk[i]), inputs[i]);
             printf("%d/%d decomposing %s\r", i + 1, n_in, inputs[i]);
             i++;
-        } else if (fq) {
-            die("FASTQ without -A is outside the accelerated path", inputs[i]);
+        } else if (fq) {            /* fastq2co() + write_fqco2file() (command_dist.c:386-387) */
+            ck(ctx, mk_fastq_co_file(ctx, inputs[i], pipecmd, kmerqlty, kmerocrs, &sk[i]), inputs[i]);
+            printf("%d/%d decomposing %s\r", i + 1, n_in, inputs[i]);
+            i++;
         } else {
             if (abundance) {
                 abundance = false;
                 printf("Warning: close abundance mode (-A) since non-fastq file input.\n");
             }
+            ck(ctx, mk_ctx_set_dedup(ctx, dedup), "mk_ctx_set_dedup");      /* -u: uniq_fasta2co() (command_dist.c:394-395) */
             /* the file loop of run_stageI() (command_dist.c:365) as one batched call over the run of genomes */
             int j = i;
             while (j < n_in && !(has_ext(inputs[j], fq_ext) || pipecmd[0])) j++;

@@ -120,7 +120,20 @@ int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes, mk_sketch 
  * with the input.  A plain (uncompressed) file is read directly with parallel pread() instead of a pipe. */
 int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out);
 
+/* ---- FASTQ without -A (`dist -Q q -n m`): fastq2co() + write_fqco2file(), iseq2comem.c:323-419, 596-621
+ * (call site command_dist.c:386-387).  A base counts iff it is ACGT and the quality byte in the same column of
+ * the record's fourth line, compared as a signed char, is >= quality (reference default 0); codes seen at least
+ * min_occurrence times (1..14, default 1) are written in slot order, without counts.  Lines are read with
+ * fgets(.., 20000, ..) there: a line of 19999 bytes or more is refused (MK_ERR_LONG_LINE).  Undefined in the
+ * reference and here: a first record without its four lines, a quality line shorter than its sequence line. */
+int mk_fastq_co_device(mk_ctx *ctx, const void *d_text, size_t nbytes, int quality, int min_occurrence, mk_sketch *out);
+int mk_fastq_co_host(mk_ctx *ctx, const void *h_text, size_t nbytes, int quality, int min_occurrence, mk_sketch *out);
+int mk_fastq_co_file(mk_ctx *ctx, const char *path, const char *pipecmd, int quality, int min_occurrence, mk_sketch *out);
+
 /* ---- FASTA genomes (`dist` without -A; MarkerDB-build sketching) ------------------------- */
+/* mk_ctx_set_dedup(ctx, 1) = `dist -u`: the following mk_fasta_co_* calls follow uniq_fasta2co()
+ * (iseq2comem.c:729-828) and write only the codes that occur ONCE in their genome. */
+int mk_ctx_set_dedup(mk_ctx *ctx, int on);
 /* A batch of n_files FASTA texts concatenated in one buffer; file i is bytes
  * [offsets[i], offsets[i+1]).  out[i] receives the sketch of file i (counts == NULL). */
 int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_t *offsets, int n_files, mk_sketch *out);

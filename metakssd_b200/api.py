@@ -84,7 +84,8 @@ class MksParams(C.Structure):  # include/mkssd_synth.h
 EXPORTS = [
     "mk_strerror", "mk_last_error", "mk_device_count", "mk_ctx_create", "mk_ctx_destroy", "mk_ctx_info",
     "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
-    "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_fasta_co_files", "mk_sketch_free", "mk_composite_begin",
+    "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_fasta_co_files", "mk_fastq_co_device",
+    "mk_fastq_co_host", "mk_fastq_co_file", "mk_ctx_set_dedup", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
     "mk_composite_component_resident", "mk_composite_component_last", "mk_format_species_coverage",
     "mk_fastq_partial_device", "mk_fastq_partial_host",
@@ -128,6 +129,10 @@ def load():
     L.mk_fasta_co_host.argtypes = [vp, vp, vp, i32, C.POINTER(MkSketch)]
     L.mk_fasta_co_file.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(MkSketch)]
     L.mk_fasta_co_files.argtypes = [vp, vp, i32, C.c_char_p, C.POINTER(MkSketch)]
+    L.mk_fastq_co_device.argtypes = [vp, vp, sz, i32, i32, C.POINTER(MkSketch)]
+    L.mk_fastq_co_host.argtypes = [vp, vp, sz, i32, i32, C.POINTER(MkSketch)]
+    L.mk_fastq_co_file.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32, C.POINTER(MkSketch)]
+    L.mk_ctx_set_dedup.argtypes = [vp, i32]
     L.mk_sketch_free.argtypes = [C.POINTER(MkSketch)]
     L.mk_sketch_free.restype = None
     L.mk_composite_begin.argtypes = [vp, i32]
@@ -333,6 +338,27 @@ class Sketcher:
         sk = MkSketch()
         self._ck(self._L.mk_fastq_koc_file(self._h, path.encode(), pipecmd.encode(), C.byref(sk)))
         return _take_sketch(sk, True)
+
+    # -- FASTQ without -A (`dist -Q q -n m`)
+    def fastq_co_device(self, d_text, nbytes: int, quality: int = 0, min_occurrence: int = 1) -> Sketch:
+        sk = MkSketch()
+        self._ck(self._L.mk_fastq_co_device(self._h, _ptr(d_text), nbytes, quality, min_occurrence, C.byref(sk)))
+        return _take_sketch(sk, False)
+
+    def fastq_co_host(self, text, quality: int = 0, min_occurrence: int = 1) -> Sketch:
+        a = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        sk = MkSketch()
+        self._ck(self._L.mk_fastq_co_host(self._h, a.ctypes.data, a.size, quality, min_occurrence, C.byref(sk)))
+        return _take_sketch(sk, False)
+
+    def fastq_co_file(self, path: str, pipecmd: str = "", quality: int = 0, min_occurrence: int = 1) -> Sketch:
+        sk = MkSketch()
+        self._ck(self._L.mk_fastq_co_file(self._h, path.encode(), pipecmd.encode(), quality, min_occurrence, C.byref(sk)))
+        return _take_sketch(sk, False)
+
+    def set_dedup(self, on: bool):
+        """`dist -u`: the following fasta_co_* calls keep only codes that occur once in their genome."""
+        self._ck(self._L.mk_ctx_set_dedup(self._h, 1 if on else 0))
 
     # -- FASTA
     def fasta_co_device(self, d_text, offsets) -> list:

@@ -310,6 +310,59 @@ extern "C" int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes,
     return rc;
 }
 
+// ---- FASTQ without -A (`dist -Q q -n m`) ---------------------------------------------------------------
+// fastq2co() + write_fqco2file() (iseq2comem.c:323-419, 596-621): the same k-mer arithmetic and slot table as the -A
+// path with (a) a per-base quality threshold, (b) lines read with fgets(.., 20000, ..), (c) a record after the first
+// used only if its fourth line ended with a newline, (d) only codes seen at least m times written, without counts.
+struct FqCoScope {       // the per-call options live in the context only while the call runs
+    mk_ctx *ctx;
+    FqCoScope(mk_ctx *c, int q, int m) : ctx(c) { c->verify_quality = q; c->line_limit = 19999; c->emit_lo = (u32)m; c->emit_hi = 0xFFFFFFFFu; }
+    ~FqCoScope() { ctx->verify_quality = INT_MIN; ctx->line_limit = 4095; ctx->emit_lo = 0; ctx->emit_hi = 0xFFFFFFFFu; }
+};
+
+extern "C" int mk_fastq_co_device(mk_ctx *ctx, const void *d_text, size_t nbytes, int quality, int min_occurrence, mk_sketch *out)
+{
+    if (!ctx || !out || (!d_text && nbytes)) return MK_ERR_ARG;
+    if (min_occurrence < 1 || min_occurrence >= 15) {        // fastq2co(): "Occurence num should smaller than 15"
+        snprintf(ctx->err, sizeof(ctx->err), "fastq2co(): Occurence num should smaller than 15");
+        return MK_ERR_ARG;
+    }
+    memset(out, 0, sizeof(*out));
+    CK(cudaSetDevice(ctx->device));
+    FqCoScope scope(ctx, quality, min_occurrence);
+    u64 *cc = nullptr, *cp = nullptr, n_cand = 0, n_newlines = 0;
+    CKR(mk_stream_fastq(ctx, (const uint8_t *)d_text, nbytes, 0, 0, false, &cc, &cp, &n_cand, &n_newlines));
+    long long keep_below = LLONG_MAX;
+    CKR(mk_tail_cut_fq2co(ctx, (const uint8_t *)d_text, nbytes, n_newlines, &keep_below));
+    ctx->pos_bits = bits_for((u64)nbytes);
+    int rc = mk_finalize_candidates(ctx, cc, cp, n_cand, keep_below, nullptr, 1, false, out);
+    ctx->pos_bits = 64;
+    if (rc != MK_OK) mk_sketch_free(out);
+    return rc;
+}
+
+extern "C" int mk_fastq_co_host(mk_ctx *ctx, const void *h_text, size_t nbytes, int quality, int min_occurrence, mk_sketch *out)
+{
+    if (!ctx || !out || (!h_text && nbytes)) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint8_t *d = nullptr;
+    CKR(mk_scratch(ctx, SB_TEXT, nbytes + 256, &d));
+    CK(cudaMemsetAsync(d + nbytes, 0, 64, ctx->stream));
+    ctx->h_src = (const uint8_t *)h_text;
+    ctx->h_src_all = (const uint8_t *)h_text;
+    int rc = mk_fastq_co_device(ctx, d, nbytes, quality, min_occurrence, out);
+    ctx->h_src = nullptr;
+    ctx->h_src_all = nullptr;
+    return rc;
+}
+
+extern "C" int mk_ctx_set_dedup(mk_ctx *ctx, int on)
+{
+    if (!ctx) return MK_ERR_ARG;
+    ctx->fasta_dedup = on != 0;
+    return MK_OK;
+}
+
 // ---- FASTA ----------------------------------------------------------------------------------------
 extern "C" int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_t *offsets, int n_files, mk_sketch *out)
 {
@@ -331,7 +384,9 @@ extern "C" int mk_fasta_co_device(mk_ctx *ctx, const void *d_text, const uint64_
     CKR(mk_stream_fastq(ctx, dense, (size_t)dense_bytes, 0, 0, true, &cc, &cp, &n_cand, nullptr));
     pc.mark("stream+verify");
     ctx->pos_bits = bits_for(dense_bytes);
+    if (ctx->fasta_dedup) { ctx->emit_lo = 1; ctx->emit_hi = 1; }      // `dist -u`: uniq_fasta2co() (iseq2comem.c:729-828)
     int rc = mk_finalize_candidates(ctx, cc, cp, n_cand, LLONG_MAX, d_dense_off, n_files, false, out);
+    ctx->emit_lo = 0; ctx->emit_hi = 0xFFFFFFFFu;
     pc.mark("finalize");
     ctx->pos_bits = 64;
     if (rc != MK_OK)

@@ -7,6 +7,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <vector>
+#include <limits.h>
 #include "mkssd_b200.h"
 
 typedef unsigned long long u64;
@@ -77,6 +78,11 @@ struct mk_ctx {
     u32 bitmap3_words = 0;
     u64 *d_ptab = nullptr;
     bool no_tables = false;         // context created without a permutation (composite only)
+    // per-call options of the secondary sketchers (reset by the entry points that set them)
+    int verify_quality = INT_MIN;   // fastq2co(): a base counts iff (signed char)quality byte >= Q (INT_MIN: no check)
+    u32 line_limit = 4095;          // fgets(buf, LEN): a line of LEN - 1 bytes or more is split by the reference
+    u32 emit_lo = 0, emit_hi = 0xFFFFFFFFu;   // codes are written iff emit_lo <= occurrences <= emit_hi
+    bool fasta_dedup = false;       // `dist -u`: uniq_fasta2co(), codes occurring once per genome
     void *d_trace = nullptr;        // development aid: phase timestamps of CTA 0 (mk_debug_set_trace)
     Scratch sb[SB_NUM];
     void *h_pinned = nullptr;       // small pinned staging block
@@ -216,5 +222,6 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
 int mk_composite_reserve(mk_ctx *ctx, u64 extra);
 int mk_composite_component_dev(mk_ctx *ctx, int component, const u32 *d_qry, const uint16_t *d_qcnt, u64 q);
 int mk_tail_cut(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, long long *keep_below);
+int mk_tail_cut_fq2co(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 n_newlines, long long *keep_below);
 int mk_fasta_compact(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, const u64 *h_offsets, int n_files,
                      uint8_t **d_dense, u64 *dense_bytes, u64 **d_dense_off);

@@ -380,6 +380,45 @@ extern "C" int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipe
     }
 }
 
+// ---- FASTQ without -A from a file / pipe ---------------------------------------------------------------
+// The quality line of a record must sit in the same buffer as its sequence line, so this secondary path reads the
+// whole (decompressed) text into host memory first and uploads it chunk by chunk under the kernel.
+extern "C" int mk_fastq_co_file(mk_ctx *ctx, const char *path, const char *pipecmd, int quality, int min_occurrence, mk_sketch *out)
+{
+    if (!ctx || !path || !out) return MK_ERR_ARG;
+    try {
+        Source src;
+        CKR(src.open_path(ctx, path, pipecmd));
+        std::vector<uint8_t> buf;
+        size_t n = 0;
+        if (src.direct) {
+            buf.resize((size_t)src.size + 64);
+            n = read_direct(src, buf.data(), (size_t)src.size, 0, default_threads());
+            if (n != src.size) {
+                snprintf(ctx->err, sizeof(ctx->err), "read error on %s", path);
+                return MK_ERR_IO;
+            }
+        } else {
+            for (;;) {
+                if (buf.size() < n + (1u << 24)) buf.resize(buf.size() ? buf.size() * 2 : (size_t)1 << 26);
+                size_t g = read_pipe(src, buf.data() + n, buf.size() - n);
+                n += g;
+                if (g == 0) break;
+            }
+            int st = pclose(src.pipe);
+            src.pipe = nullptr; src.fd = -1;
+            if (st != 0 && n == 0) {
+                snprintf(ctx->err, sizeof(ctx->err), "%s: exit status %d and no data", src.what.c_str(), st);
+                return MK_ERR_IO;
+            }
+        }
+        return mk_fastq_co_host(ctx, buf.data(), n, quality, min_occurrence, out);
+    } catch (const std::bad_alloc &) {
+        snprintf(ctx->err, sizeof(ctx->err), "out of host memory while reading %s", path);
+        return MK_ERR_NOMEM;
+    }
+}
+
 // ---- FASTA genomes from files ----------------------------------------------------------------------
 // Whole files (a genome is a few MB) are read into one pinned batch buffer by a pool of reader threads and
 // sketched with one mk_fasta_co_device call per batch of at most MK_FASTA_BATCH_BYTES of text.

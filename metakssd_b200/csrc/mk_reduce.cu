@@ -395,9 +395,13 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
     uint16_t *h_cnt = (uint16_t *)((char *)stage + seg_bytes + code_bytes);
     CK(cudaMemcpyAsync(h_seg, seg_start, (size_t)nseg * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(h_code, out_code, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (with_counts) CK(cudaMemcpyAsync(h_cnt, out_cnt, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    // occurrence filter of the secondary sketchers (`dist -n M` keeps codes seen at least M times, `dist -u` codes seen
+    // once): every distinct code took part in the slot reconstruction, like in the reference's table; the filter
+    // only decides what is written (write_fqco2file(), wrt_co2cmpn_use_inn_subctx(): iseq2comem.c:611, :640)
+    const bool filtered = ctx->emit_lo > 1 || ctx->emit_hi != 0xFFFFFFFFu;
+    if (with_counts || filtered) CK(cudaMemcpyAsync(h_cnt, out_cnt, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->prof.d2h_bytes += nseg * 8 + n * 4 + (with_counts ? n * 2 : 0);
+    ctx->prof.d2h_bytes += nseg * 8 + n * 4 + ((with_counts || filtered) ? n * 2 : 0);
     pc.mark("    d2h");
     // empty segments inherit the start of the next non-empty one
     h_seg[nseg] = n;
@@ -417,6 +421,14 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
             u64 seg = ((u64)f << cbits) | (u64)c;
             u64 lo = h_seg[seg], hi = h_seg[seg + 1];
             u64 m = hi - lo;
+            if (filtered) {        // compact in place (segments are disjoint): keep codes whose count passes
+                u64 w = lo;
+                for (u64 i = lo; i < hi; i++) {
+                    const u32 k = h_cnt[i];
+                    if (k >= ctx->emit_lo && k <= ctx->emit_hi) { h_code[w] = h_code[i]; h_cnt[w] = h_cnt[i]; w++; }
+                }
+                m = w - lo;
+            }
             s->n[c] = m;
             s->n_total += m;
             s->codes[c] = (uint32_t *)malloc((size_t)(m ? m : 1) * 4);

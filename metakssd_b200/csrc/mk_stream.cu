@@ -1192,7 +1192,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
 // position.  Text comes from global memory: ~10 hits per 24 KB tile, mostly L2 hits.
 __global__ void __launch_bounds__(256)
 k_verify(const uint8_t *__restrict__ text, u64 n, u64 pos_base, KParams kp, const u64 *__restrict__ ptab,
-         u64 *__restrict__ cand_code, u64 *__restrict__ cand_pos)
+         u64 *__restrict__ cand_code, u64 *__restrict__ cand_pos, u64 nbytes, int quality, u32 line_limit)
 {
     u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1201,6 +1201,22 @@ k_verify(const uint8_t *__restrict__ text, u64 n, u64 pos_base, KParams kp, cons
     if (pos + 1 >= (u64)kp.TL) {
         u64 c;
         if (verify_kmer(text + pos, kp, ptab, &c)) code = c;
+    }
+    if (code != ~0ull && quality != INT_MIN) {
+        // fastq2co() (iseq2comem.c:366-368): every base of the k-mer needs (signed char)quality >= Q, the quality byte
+        // being the one in the same column of the record's fourth line.  Line start: back to the previous '\n';
+        // quality line: after the second '\n' that follows the k-mer.
+        u64 a = pos;                                   // first byte of the sequence line
+        for (u32 s = 0; a > 0 && text[a - 1] != '\n' && s <= line_limit; s++) a--;
+        u64 e = pos + 1;                               // end of the sequence line
+        for (u32 s = 0; e < nbytes && text[e] != '\n' && s <= line_limit; s++) e++;
+        u64 p2 = e + 1;                                // end of the '+' line
+        for (u32 s = 0; p2 < nbytes && text[p2] != '\n' && s <= line_limit; s++) p2++;
+        const u64 qa = p2 + 1;
+        const u64 col0 = pos + 1 - (u64)kp.TL - a;
+        bool ok = e < nbytes && p2 < nbytes && qa + col0 + (u64)kp.TL <= nbytes;
+        for (int j = 0; ok && j < kp.TL; j++) ok = (int)(signed char)text[qa + col0 + (u64)j] >= quality;
+        if (!ok) code = ~0ull;
     }
     cand_code[i] = code;
     cand_pos[i] = pos_base + pos;
@@ -1229,6 +1245,46 @@ __global__ void k_tail_cut(const uint8_t *__restrict__ text, u64 n, long long *o
         hi -= 32;
     }
     if (lane == 0) *out = (nfound == 2) ? found[1] : -1;
+}
+
+// fastq2co() (iseq2comem.c:323-419) uses a record after the first only if its fourth line ended with a newline:
+// with N newlines in the text, sequence lines after newline number 4 floor(N / 4) are dropped (N < 4: only the
+// first record exists, it is always used).  One warp finds the last four newlines.
+__global__ void k_last_newlines(const uint8_t *__restrict__ text, u64 n, long long *out /*[4]*/)
+{
+    const u32 lane = threadIdx.x;
+    long long found[4] = {-1, -1, -1, -1};
+    int nfound = 0;
+    long long hi = (long long)n - 1;
+    while (hi >= 0 && nfound < 4) {
+        long long idx = hi - (long long)lane;
+        bool is_nl = idx >= 0 && text[idx] == '\n';
+        u32 m = __ballot_sync(0xffffffffu, is_nl);
+        while (m && nfound < 4) {
+            u32 l = __ffs(m) - 1;                 // smallest lane = highest offset
+            found[nfound++] = hi - (long long)l;
+            m &= m - 1;
+        }
+        hi -= 32;
+    }
+    if (lane == 0)
+        for (int i = 0; i < 4; i++) out[i] = found[i];
+}
+
+int mk_tail_cut_fq2co(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 n_newlines, long long *keep_below)
+{
+    *keep_below = LLONG_MAX;
+    if (n_newlines < 4 || nbytes == 0) return MK_OK;
+    long long *d_out, h[4];
+    CKR(mk_scratch(ctx, SB_MISC, 64, &d_out));
+    k_last_newlines<<<1, 32, 0, ctx->stream>>>(d_text, (u64)nbytes, d_out);
+    LAUNCH_COUNT(ctx);
+    CK(cudaMemcpyAsync(h, d_out, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.d2h_bytes += sizeof(h);
+    const long long cut = h[n_newlines % 4];         // newline number 4 floor(N / 4), counted from the end
+    *keep_below = cut >= 0 ? cut + 1 : LLONG_MAX;
+    return MK_OK;
 }
 
 int mk_tail_cut(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, long long *keep_below)
@@ -1283,7 +1339,7 @@ extern "C" int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t 
 // fgets(buf, 4096) splits a line once 4095 bytes came without a newline; what the reference does with
 // the pieces depends on stale buffer contents, so such input is refused.  A run of >= 4095 newline-free
 // bytes covers an aligned 2 KB chunk entirely: one warp per such chunk measures the run around it.
-__global__ void __launch_bounds__(256) k_long_line_check(const uint8_t *__restrict__ text, u64 n, u32 *__restrict__ flag)
+__global__ void __launch_bounds__(256) k_long_line_check(const uint8_t *__restrict__ text, u64 n, u32 *__restrict__ flag, u64 limit)
 {
     const u32 lane = threadIdx.x & 31;
     const u64 nchunks = n / 2048;
@@ -1304,21 +1360,21 @@ __global__ void __launch_bounds__(256) k_long_line_check(const uint8_t *__restri
         if (__any_sync(0xffffffffu, any != 0)) continue;
         const u64 lo = c * 2048, hi = lo + 2048;
         u64 back = 0, fwd = 0;                       // newline-free bytes right before lo / right after hi
-        while (back < 2048 && back < lo) {
+        while (back + 2048 < limit && back < lo) {
             const u64 d = back + lane;               // looks at byte lo - 1 - d
             const bool nl = d < lo && text[lo - 1 - d] == '\n';
             const u32 m = __ballot_sync(0xffffffffu, nl);
             if (m) { back += __ffs(m) - 1; break; }
             back = back + 32 < lo ? back + 32 : lo;
         }
-        while (back + 2048 + fwd < 4095 && hi + fwd < n) {
+        while (back + 2048 + fwd < limit && hi + fwd < n) {
             const u64 p = hi + fwd + lane;
             const bool nl = p < n && text[p] == '\n';
             const u32 m = __ballot_sync(0xffffffffu, nl);
             if (m) { fwd += __ffs(m) - 1; break; }
             fwd = hi + fwd + 32 < n ? fwd + 32 : n - hi;
         }
-        if (back + 2048 + fwd >= 4095 && lane == 0) atomicOr(flag, 1u);
+        if (back + 2048 + fwd >= limit && lane == 0) atomicOr(flag, 1u);
     }
 }
 
@@ -1581,14 +1637,14 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
         if (!raw_mode && !long_line && (flags & FLAG_MAYBE_LONG)) {     // rare: measure the line exactly
             u32 *d_flag = (u32 *)(counters + 6), h_flag = 0;
             CK(cudaMemsetAsync(d_flag, 0, 4, ctx->stream));
-            k_long_line_check<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_text, (u64)nbytes, d_flag);
+            k_long_line_check<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_text, (u64)nbytes, d_flag, (u64)ctx->line_limit);
             LAUNCH_COUNT(ctx);
             CK(cudaMemcpyAsync(&h_flag, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
             long_line = h_flag != 0;
         }
         if (long_line) {
-            snprintf(ctx->err, sizeof(ctx->err), "FASTQ line of 4095 bytes or more (fgets(…, 4096) would split it)");
+            snprintf(ctx->err, sizeof(ctx->err), "FASTQ line of %u bytes or more (fgets(…, %u) would split it)", ctx->line_limit, ctx->line_limit + 1);
             return MK_ERR_LONG_LINE;
         }
         if (h[0] > cap) { // candidate buffer too small: size it exactly and run again
@@ -1596,7 +1652,8 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
             continue;
         }
         if (h[0]) {
-            k_verify<<<(unsigned)((h[0] + 255) / 256), 256, 0, ctx->stream>>>(d_text, h[0], pos_base, kp, ctx->d_ptab, cc, cp);
+            k_verify<<<(unsigned)((h[0] + 255) / 256), 256, 0, ctx->stream>>>(d_text, h[0], pos_base, kp, ctx->d_ptab, cc, cp, (u64)nbytes,
+                                                                             ctx->verify_quality, ctx->line_limit);
             LAUNCH_COUNT(ctx);
             CK(cudaGetLastError());
         }

@@ -67,6 +67,10 @@ def lib():
         for fn in (L.ko_fastq_koc, L.ko_fasta_co):
             fn.argtypes = [C.POINTER(KoParams), C.c_void_p, C.c_void_p, C.c_size_t]
             fn.restype = C.POINTER(KoSketch)
+        L.ko_fastq_co.argtypes = [C.POINTER(KoParams), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        L.ko_fastq_co.restype = C.POINTER(KoSketch)
+        L.ko_fasta_co_uniq.argtypes = [C.POINTER(KoParams), C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ko_fasta_co_uniq.restype = C.POINTER(KoSketch)
         L.ko_sketch_free.argtypes = [C.POINTER(KoSketch)]
         L.ko_composite_component.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -200,6 +204,18 @@ def fasta_co(p: KoParams, perm: np.ndarray, text) -> Sketch:
     return _take(lib().ko_fasta_co(C.byref(p), perm.ctypes.data, t.ctypes.data, t.size), False)
 
 
+def fastq_co(p: KoParams, perm: np.ndarray, text, quality: int = 0, min_occurrence: int = 1) -> Sketch:
+    """`dist` on FASTQ without -A: fastq2co(.., Q, M) + write_fqco2file() (iseq2comem.c:323-419, 596-621)."""
+    t = _as_bytes(text)
+    return _take(lib().ko_fastq_co(C.byref(p), perm.ctypes.data, t.ctypes.data, t.size, quality, min_occurrence), False)
+
+
+def fasta_co_uniq(p: KoParams, perm: np.ndarray, text) -> Sketch:
+    """`dist -u` on FASTA: uniq_fasta2co() (iseq2comem.c:729-828), codes occurring once in the file."""
+    t = _as_bytes(text)
+    return _take(lib().ko_fasta_co_uniq(C.byref(p), perm.ctypes.data, t.ctypes.data, t.size), False)
+
+
 # --------------------------------------------------------------------------- composite
 def composite(ref_comp, ref_names, qry_comp, qry_name: str) -> str:
     """ref_comp: list over components of (codes uint32, index uint64[S+1]);
@@ -299,9 +315,9 @@ def run_ref(args, cwd=None, threads_env=None) -> subprocess.CompletedProcess:
     return subprocess.run([REF_BIN] + list(args), cwd=cwd, env=env, capture_output=True, text=True, check=True)
 
 
-def ref_dist(shuf_path: str, inputs, outdir: str, abundance: bool, p: int = 1) -> SketchDir:
-    """`metakssd dist -L <shuf> [-A] -p <p> -o <outdir> <inputs...>` with the reference binary."""
-    args = ["dist", "-L", shuf_path, "-p", str(p), "-o", outdir]
+def ref_dist(shuf_path: str, inputs, outdir: str, abundance: bool, p: int = 1, extra=()) -> SketchDir:
+    """`metakssd dist -L <shuf> [-A] [extra flags] -p <p> -o <outdir> <inputs...>` with the reference binary."""
+    args = ["dist", "-L", shuf_path, "-p", str(p), "-o", outdir] + list(extra)
     if abundance:
         args.append("-A")
     run_ref(args + list(inputs))

@@ -293,6 +293,160 @@ ko_sketch *ko_fasta_co(const ko_params *p, const int32_t *shuf, const char *text
     return out;
 }
 
+/* ---------------- FASTQ without -A: fastq2co() + write_fqco2file() -------------------------------
+ * iseq2comem.c:323-419: the first record is read unconditionally (four fgets(.., LEN = 20000, ..)); every further
+ * record is read when the previous sequence line ends and is used only if feof() is still false after its four
+ * fgets() calls, i.e. its fourth line ended with a newline.  A base counts iff it is ACGT and the quality byte in
+ * the same column, compared as a (signed) char, is >= Q.  Table entries are code << 4 | count; CT_MAX (15) in the
+ * low bits marks "occurred at least M times" (set at once when M == 1); write_fqco2file() (:596-621) writes the
+ * marked codes in ascending slot order, no counts.  keycount is never incremented in the reference, so the
+ * "too crowd" error cannot fire.  A line of LEN - 1 = 19999 bytes or more is split by fgets: status 2. */
+typedef struct { const char *t; size_t n, at; int eof; } ko_reader;
+static int rd_fgets(ko_reader *r, char *buf, int size, int *too_long)
+{
+    int len = 0;
+    while (len < size - 1) {
+        if (r->at >= r->n) { r->eof = 1; break; }
+        char c = r->t[r->at++];
+        buf[len++] = c;
+        if (c == '\n') break;
+    }
+    if (len == 0) return 0;                 /* NULL: the buffer keeps its old content */
+    if (len == size - 1 && buf[len - 1] != '\n') *too_long = 1;
+    buf[len] = 0;
+    return 1;
+}
+
+ko_sketch *ko_fastq_co(const ko_params *p, const int32_t *shuf, const char *text, size_t n, int Q, int M)
+{
+    enum { LEN = 20000 };
+    ko_sketch *out = (ko_sketch *)calloc(1, sizeof(ko_sketch));
+    ko_table T;
+    if (!out || table_init(&T, p->hashsize)) return NULL;
+    char *seq = (char *)calloc(LEN + 10, 1), *qual = (char *)calloc(LEN + 10, 1);
+    ko_reader R = {text, n, 0, 0};
+    int too_long = 0;
+    rd_fgets(&R, seq, LEN, &too_long); rd_fgets(&R, seq, LEN, &too_long);
+    rd_fgets(&R, qual, LEN, &too_long); rd_fgets(&R, qual, LEN, &too_long);
+    int base = 1;
+    u64 fwd = 0, rc = 0;
+    int sl = (int)strlen(seq);
+    for (int pos = 0; pos < sl; pos++) {
+        if (too_long) { out->status = 2; break; }
+        if (seq[pos] == '\n') {
+            rd_fgets(&R, seq, LEN, &too_long); rd_fgets(&R, seq, LEN, &too_long);
+            rd_fgets(&R, qual, LEN, &too_long); rd_fgets(&R, qual, LEN, &too_long);
+            sl = (int)strlen(seq);
+            if (!R.eof) { base = 1; pos = -1; continue; }
+            break;
+        }
+        int b = base_code((unsigned char)seq[pos]);
+        if (b >= 0 && qual[pos] >= Q) {        /* char comparison: bytes >= 0x80 are negative */
+            fwd = ((fwd << 2) | (u64)b) & p->tupmask;
+            rc = (rc >> 2) + (((u64)b ^ 3ull) << p->crvs_shift);
+            base++;
+        } else { base = 1; continue; }
+        if (base <= p->TL) continue;
+        long long c = kmer_to_code(p, shuf, fwd, rc);
+        if (c < 0) continue;
+        u64 code = (u64)c;
+        u64 h1 = code % p->hashsize, h2 = 1 + code % (p->hashsize - 1);
+        for (u64 i2 = 0; i2 < p->hashsize; i2++) {
+            uint32_t slot = (uint32_t)((h1 + i2 * h2) % p->hashsize);
+            if (T.tab[slot] == 0) {
+                T.tab[slot] = M == 1 ? ((code << 4) | 15ull) : ((code << 4) + 1ull);
+                table_note_used(&T, slot);
+                break;
+            }
+            if ((T.tab[slot] >> 4) == code) {
+                if ((T.tab[slot] & 15ull) == 15ull) break;
+                T.tab[slot] += 1;
+                if (!((T.tab[slot] & 15ull) < (u64)M)) T.tab[slot] |= 15ull;
+                break;
+            }
+        }
+    }
+    if (too_long) out->status = 2;
+    qsort(T.used, T.n_used, sizeof(uint32_t), cmp_u32);
+    out->codes = (u64 *)malloc(sizeof(u64) * (T.n_used + 1));
+    out->slots = (uint32_t *)malloc(sizeof(uint32_t) * (T.n_used + 1));
+    size_t m = 0;
+    for (size_t i = 0; i < T.n_used; i++) {
+        u64 e = T.tab[T.used[i]];
+        if ((e & 15ull) != 15ull) continue;
+        out->codes[m] = e >> 4;
+        out->slots[m] = T.used[i];
+        m++;
+    }
+    out->n = m;
+    free(seq); free(qual);
+    table_free(&T);
+    return out;
+}
+
+/* ---------------- FASTA with -u: uniq_fasta2co() + wrt_co2cmpn_use_inn_subctx() -------------------
+ * iseq2comem.c:729-828: the tokenizer and arithmetic of fasta2co(); a code met again gets bit 63 set, and the
+ * writer (:640) skips entries with that bit: only codes occurring ONCE in the file are written, in the slot
+ * order all distinct codes produced.  Code 0 looks like an empty slot and is lost, as in fasta2co(). */
+ko_sketch *ko_fasta_co_uniq(const ko_params *p, const int32_t *shuf, const char *text, size_t n)
+{
+    const u64 HI = 0x8000000000000000ull;
+    ko_sketch *out = (ko_sketch *)calloc(1, sizeof(ko_sketch));
+    ko_table T;
+    if (!out || table_init(&T, p->hashsize)) return NULL;
+    uint32_t keycount = 0;
+    long long base = 1;
+    u64 fwd = 0, rc = 0;
+    for (size_t i = 0; i < n; i++) {
+        unsigned char ch = (unsigned char)text[i];
+        int b = base_code(ch);
+        if (b >= 0) {
+            fwd = ((fwd << 2) | (u64)b) & p->tupmask;
+            rc = (rc >> 2) + (((u64)b ^ 3ull) << p->crvs_shift);
+            base++;
+        } else if (ch == '\n' || ch == '\r') {
+            continue;
+        } else if (ch == '>') {
+            while (i < n && text[i] != '\n') i++;
+            base = 1;
+            continue;
+        } else {
+            base = 1;
+            continue;
+        }
+        if (base <= p->TL) continue;
+        long long c = kmer_to_code(p, shuf, fwd, rc);
+        if (c < 0) continue;
+        u64 code = (u64)c;
+        u64 h1 = code % p->hashsize, h2 = 1 + code % (p->hashsize - 1);
+        for (u64 i2 = 0; i2 < p->hashsize; i2++) {
+            uint32_t slot = (uint32_t)((h1 + i2 * h2) % p->hashsize);
+            if (T.tab[slot] == 0) {
+                T.tab[slot] = code;
+                if (code != 0) table_note_used(&T, slot);
+                if (++keycount > p->hashlimit) out->status = 1;
+                break;
+            }
+            if ((T.tab[slot] | HI) == (code | HI)) { T.tab[slot] |= HI; break; }
+        }
+        if (out->status) break;
+    }
+    qsort(T.used, T.n_used, sizeof(uint32_t), cmp_u32);
+    out->codes = (u64 *)malloc(sizeof(u64) * (T.n_used + 1));
+    out->slots = (uint32_t *)malloc(sizeof(uint32_t) * (T.n_used + 1));
+    size_t m = 0;
+    for (size_t i = 0; i < T.n_used; i++) {
+        u64 e = T.tab[T.used[i]];
+        if (e & HI) continue;
+        out->codes[m] = e;
+        out->slots[m] = T.used[i];
+        m++;
+    }
+    out->n = m;
+    table_free(&T);
+    return out;
+}
+
 /* Split a sketch into the per-component file arrays of write_fqkoc2files / wrt_co2cmpn:
  * component = code % component_num, file value = (uint32)(code >> comp_code_bits).
  * comp_of[i] receives the component, filecode[i] the 32-bit value. */

@@ -66,3 +66,70 @@ def fastq_cases():
     base = edge_base()
     for name, text in _edge_variants(base):
         yield "edge_" + name, (11, 6, 3, 1234), np.frombuffer(text, dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# round 2: `dist` on FASTQ without -A (fastq2co: -Q / -n) and `dist -u` (uniq_fasta2co);
+# vectors in tests/golden/reference_vectors_r2.npz (tests/golden/make_golden_r2.py)
+def _vary_quality(fq: bytes, seed: int) -> bytes:
+    """Quality lines with a spread of values: most bytes high, runs of low ones, a few bytes >= 0x80 (negative as
+    a signed char, so they fail even Q = 0)."""
+    rng = np.random.default_rng(seed)
+    lines = fq.split(b"\n")
+    for i in range(3, len(lines), 4):
+        q = np.frombuffer(lines[i], dtype=np.uint8).copy()
+        if q.size == 0:
+            continue
+        n_low = int(rng.integers(0, 4))
+        for _ in range(n_low):
+            a = int(rng.integers(0, q.size))
+            q[a:a + int(rng.integers(1, 12))] = int(rng.integers(33, 60))
+        if rng.random() < 0.05:
+            q[int(rng.integers(0, q.size))] = 0x80 + int(rng.integers(0, 100))
+        lines[i] = q.tobytes()
+    return b"\n".join(lines)
+
+
+def fastq_co_cases():
+    """(name, (k, subk, L, shuf_seed), text, Q, M)"""
+    S = O.synth(77, 8, 120_000, 150)
+    base = _vary_quality(bytes(S.fastq(0, 12_000)), 5)
+    geo = (11, 6, 3, 1234)
+    for Q, M in ((0, 1), (40, 1), (0, 2), (45, 3), (70, 1)):
+        yield "fqco_q%d_n%d" % (Q, M), geo, base, Q, M
+    # tails: 1500 reads with varied quality + one record (quality all 'I') that contributes codes found nowhere else,
+    # so that every rule about the last record changes the sketch
+    eb = edge_base().rstrip(b"\n").split(b"\n")
+    special = b"\n".join(eb[-4:]) + b"\n"
+    head = _vary_quality(b"\n".join(eb[:-4]) + b"\n", 6)
+    tbase = head + special
+    lines = tbase.split(b"\n")
+    first = b"\n".join(head.split(b"\n")[:4]) + b"\n"
+    tails = {
+        "as_is": tbase,
+        "no_final_newline": tbase[:-1],
+        "missing_quality": b"\n".join(lines[:-2]) + b"\n",
+        "seq_unterminated": b"\n".join(lines[:-3]),
+        "extra_header": tbase + b"@tail\n",
+        "extra_three_lines": tbase + b"@tail\nACGTACGTACGTACGTACGTACGTACGTACGTACGT\n+\n",
+        "crlf": tbase.replace(b"\n", b"\r\n"),
+        "one_record": special,
+        "one_record_unterminated": special[:-1],
+        "two_records_second_unterminated": first + special[:-1],
+        "two_records": first + special,
+    }
+    for name, text in tails.items():
+        yield "fqco_tail_" + name, geo, text, 40, 1
+    yield "fqco_l2k11", (11, 5, 2, 2234), _vary_quality(bytes(S.fastq(100, 3_100)), 9), 45, 2
+
+
+def uniq_cases():
+    """(name, (k, subk, L, shuf_seed), fasta text) for `dist -u`"""
+    S = O.synth(78, 6, 150_000, 150)
+    for s in range(3):
+        g = bytes(S.fasta(s))
+        body = g.split(b"\n", 1)[1]
+        # the genome followed by a copy of part of it: the codes of that part occur twice
+        yield "uniq_sp%d" % s, (11, 6, 3, 1234), g + b">copy\n" + body[: len(body) * (s + 1) // 4]
+    yield "uniq_plain", (11, 6, 3, 1234), bytes(S.fasta(4))
+    yield "uniq_l2k11", (11, 5, 2, 2234), bytes(S.fasta(5)) + b">c\n" + bytes(S.fasta(5)).split(b"\n", 1)[1][:40_000]

@@ -11,6 +11,7 @@
  *   metakssd-b200 dist -L L3K11.shuf -A -o sketch reads.fq [more inputs ...]
  *   metakssd-b200 dist -L L3K11.shuf -o gsk [-u] sp1.fasta sp2.fasta ...
  *   metakssd-b200 dist -L L3K11.shuf -o sk [-Q 20] [-n 2] reads.fq        (no -A: fastq2co)
+ *   metakssd-b200 set -g group_name.txt -o pan gsk ; set -q -o union_sp pan ; set -i union_sp -o markerdb pan
  *   metakssd-b200 composite -r markerdb -q sketch > species_coverage.tsv
  *
  * Differences from the reference, all outside the sketch content: input files keep their command
@@ -248,6 +249,196 @@ static int cmd_dist(int argc, char **argv)
     return 0;
 }
 
+/* ---- set -g / -q / -i ----------------------------------------------------------------------- */
+/* The MarkerDB pipeline of the reference (README: dist -> set -g -> set -q -> set -i), directory formats and taxon
+ * order as command_set.c writes them; the unions / filters run on the device (mk_set_group, mk_set_uniq_union,
+ * mk_set_operate). */
+static int next_prime(int n)                         /* global_basic.c:453-475 */
+{
+    for (;;) {
+        int composite = 0;
+        for (int j = 2; (long long)j * j <= n; j++)
+            if (n % j == 0) { composite = 1; break; }
+        if (!composite) return n;
+        n++;
+    }
+}
+typedef struct { int taxid; char *name; int first_line; } taxon_t;
+
+/* organize_taxf() (command_set.c:635-704): taxa in ascending slot of a table of nextPrime(lines / 0.6) slots */
+static int read_taxfile(const char *path, int **taxon_of_line, taxon_t **taxa, int *n_lines)
+{
+    size_t nb;
+    char *raw = slurp(path, &nb);
+    int ln = 0;
+    for (size_t i = 0; i < nb; i++) ln += raw[i] == '\n';
+    int hashsz = next_prime((int)((double)ln / 0.6));
+    taxon_t *tab = calloc((size_t)(hashsz > 0 ? hashsz : 1), sizeof *tab);
+    for (int i = 0; i < hashsz; i++) tab[i].taxid = -1;
+    int *slot_of = malloc(sizeof(int) * (size_t)(ln > 0 ? ln : 1));
+    size_t at = 0;
+    for (int i = 0; i < ln; i++) {
+        size_t e = at;
+        while (raw[e] != '\n') e++;
+        if (e - at >= PATHLEN - 1) die("organize_taxf(): taxfile line exceeds PATHLEN", path);
+        raw[e] = 0;
+        char *line = raw + at;
+        at = e + 1;
+        char *tab1 = strchr(line, '\t');
+        char *name = NULL;
+        if (tab1) { *tab1 = 0; name = tab1 + 1; char *t2 = strchr(name, '\t'); if (t2) *t2 = 0; if (!*name) name = NULL; }
+        int taxid = atoi(line);
+        slot_of[i] = -1;
+        for (int n = 0; n < hashsz; n++) {
+            int hv = (taxid % hashsz + n * (1 + taxid % (hashsz - 1))) % hashsz;
+            if (tab[hv].taxid == -1) { tab[hv].taxid = taxid; tab[hv].name = name ? strdup(name) : NULL; tab[hv].first_line = i; slot_of[i] = hv; break; }
+            if (tab[hv].taxid == taxid) {
+                if ((tab[hv].name == NULL) != (name == NULL) || (name && strcmp(tab[hv].name, name)))
+                    die("organize_taxf() abort!: a taxid has different taxnames", path);
+                slot_of[i] = hv;
+                break;
+            }
+        }
+    }
+    int n_taxa = 0;
+    int *pos_of_slot = malloc(sizeof(int) * (size_t)(hashsz > 0 ? hashsz : 1));
+    *taxa = calloc((size_t)(ln > 0 ? ln : 1), sizeof **taxa);
+    for (int i = 0; i < hashsz; i++)
+        if (tab[i].taxid != -1) { (*taxa)[n_taxa] = tab[i]; pos_of_slot[i] = n_taxa++; }
+    *taxon_of_line = malloc(sizeof(int) * (size_t)(ln > 0 ? ln : 1));
+    for (int i = 0; i < ln; i++) (*taxon_of_line)[i] = slot_of[i] < 0 ? -1 : pos_of_slot[slot_of[i]];
+    *n_lines = ln;
+    free(tab); free(slot_of); free(pos_of_slot); free(raw);
+    return n_taxa;
+}
+
+static mk_ctx *plain_ctx(const co_dstat_t *st)
+{
+    int k = st->kmerlen / 2, drl = st->dim_rd_len / 2;
+    int subk = drl + 3 > k ? k : drl + 3;
+    mk_ctx *ctx = NULL;
+    ck(NULL, mk_ctx_create(&ctx, NULL, k, subk, drl, 0), "mk_ctx_create");
+    return ctx;
+}
+static void write_file(const char *dir, const char *name, int c, const void *p, size_t bytes)
+{
+    char path[PATHLEN * 2];
+    if (c >= 0) snprintf(path, sizeof path, "%s/%s.%d", dir, name, c); else snprintf(path, sizeof path, "%s/%s", dir, name);
+    FILE *f = fopen(path, "wb");
+    if (!f || (bytes && fwrite(p, bytes, 1, f) != 1)) die("cannot write", path);
+    fclose(f);
+}
+
+static int cmd_set(int argc, char **argv)
+{
+    const char *taxfile = NULL, *outdir = "./", *pan = NULL, *in = NULL;
+    int op = -1;                     /* 3 = -q, 1 = -i, 0 = -s, 5 = -g */
+    for (int i = 0; i < argc; i++) {
+        if (!strcmp(argv[i], "-g") && i + 1 < argc) { taxfile = argv[++i]; if (op == -1) op = 5; }
+        else if (!strcmp(argv[i], "-q")) { if (op == -1) op = 3; }
+        else if (!strcmp(argv[i], "-i") && i + 1 < argc) { pan = argv[++i]; if (op == -1) op = 1; }
+        else if (!strcmp(argv[i], "-s") && i + 1 < argc) { pan = argv[++i]; if (op == -1) op = 0; }
+        else if (!strcmp(argv[i], "-o") && i + 1 < argc) outdir = argv[++i];
+        else if (!strcmp(argv[i], "-p") && i + 1 < argc) ++i;
+        else if (argv[i][0] == '-') die("option not on the hot path", argv[i]);
+        else in = argv[i];
+    }
+    if (!in || op == -1) die("set operation use : -g, -q, -i or -s", NULL);
+    char path[PATHLEN * 2];
+    snprintf(path, sizeof path, "%s/cofiles.stat", in);
+    size_t stat_bytes;
+    char *stat_raw = slurp(path, &stat_bytes);
+    co_dstat_t st;
+    memcpy(&st, stat_raw, sizeof st);
+    mk_ctx *ctx = plain_ctx(&st);
+    mkdir(outdir, 0777);
+    size_t b;
+    if (op == 5) {                                       /* grouping_genomes(), command_set.c:831-1003 */
+        int *taxon_of_line, n_lines;
+        taxon_t *taxa;
+        int n_all = read_taxfile(taxfile, &taxon_of_line, &taxa, &n_lines);
+        if (n_lines != st.infile_num) die("grouping_genomes(): genome number of the sketch does not match the taxfile", taxfile);
+        /* taxid 0 is ignored: its genomes are skipped and its position drops out of the output */
+        int *out_pos = malloc(sizeof(int) * (size_t)(n_all > 0 ? n_all : 1)), n_taxa = 0;
+        for (int t = 0; t < n_all; t++) out_pos[t] = taxa[t].taxid == 0 ? -1 : n_taxa++;
+        int32_t *taxon_of = malloc(sizeof(int32_t) * (size_t)n_lines);
+        for (int g = 0; g < n_lines; g++) taxon_of[g] = taxon_of_line[g] < 0 ? -1 : out_pos[taxon_of_line[g]];
+        unsigned int *ctx_ct = calloc((size_t)(n_taxa > 0 ? n_taxa : 1), sizeof *ctx_ct);
+        unsigned long long all_ct = 0;
+        uint64_t *oi = malloc(sizeof(uint64_t) * (size_t)(n_taxa + 1));
+        for (int c = 0; c < st.comp_num; c++) {
+            snprintf(path, sizeof path, "%s/combco.%d", in, c);
+            uint32_t *codes = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.index.%d", in, c);
+            uint64_t *index = slurp(path, &b);
+            uint32_t *oc = NULL;
+            if (n_taxa > 0) ck(ctx, mk_set_group(ctx, codes, index, n_lines, taxon_of, n_taxa, &oc, oi), "mk_set_group");
+            else oi[0] = 0;
+            write_file(outdir, "combco", c, oc, (size_t)oi[n_taxa] * 4);
+            write_file(outdir, "combco.index", c, oi, sizeof(uint64_t) * (size_t)(n_taxa + 1));
+            for (int t = 0; t < n_taxa; t++) ctx_ct[t] += (unsigned)(oi[t + 1] - oi[t]);
+            all_ct += oi[n_taxa];
+            mk_free(oc); free(codes); free(index);
+        }
+        st.infile_num = n_taxa; st.koc = 0; st.all_ctx_ct = all_ct;
+        snprintf(path, sizeof path, "%s/cofiles.stat", outdir);
+        FILE *f = fopen(path, "wb");
+        if (!f) die("cannot write", path);
+        memcpy(stat_raw, &st, sizeof st);                 /* (keeps the input's padding bytes like the reference's fread/fwrite) */
+        fwrite(stat_raw, sizeof st, 1, f);
+        fwrite(ctx_ct, sizeof *ctx_ct, (size_t)n_taxa, f);
+        for (int t = 0; t < n_all; t++) {
+            if (taxa[t].taxid == 0) continue;
+            char name[PATHLEN];
+            memset(name, 0, sizeof name);
+            if (taxa[t].name) snprintf(name, sizeof name, "%d_%s", taxa[t].taxid, taxa[t].name);
+            else snprintf(name, sizeof name, "%d", taxa[t].taxid);
+            fwrite(name, PATHLEN, 1, f);
+        }
+        fclose(f);
+    } else if (op == 3) {                                /* uniq_sketch_union(), command_set.c:427-512 */
+        write_file(outdir, "cofiles.stat", -1, stat_raw, sizeof st);
+        for (int c = 0; c < st.comp_num; c++) {
+            snprintf(path, sizeof path, "%s/combco.%d", in, c);
+            uint32_t *codes = slurp(path, &b);
+            uint32_t *out = NULL;
+            uint64_t n_out = 0;
+            ck(ctx, mk_set_uniq_union(ctx, codes, b / 4, &out, &n_out), "mk_set_uniq_union");
+            write_file(outdir, "uniq_pan", c, out, (size_t)n_out * 4);
+            mk_free(out); free(codes);
+        }
+    } else {                                             /* sketch_operate(), command_set.c:322-423 */
+        snprintf(path, sizeof path, "%s/cofiles.stat", pan);
+        size_t pb;
+        char *pan_raw = slurp(path, &pb);
+        co_dstat_t pst;
+        memcpy(&pst, pan_raw, sizeof pst);
+        if (pst.shuf_id != st.shuf_id) die("sketcing id not match", pan);
+        unsigned int *ctx_ct = (unsigned int *)(stat_raw + sizeof st);
+        memset(ctx_ct, 0, sizeof(unsigned int) * (size_t)st.infile_num);
+        uint64_t *oi = malloc(sizeof(uint64_t) * (size_t)(st.infile_num + 1));
+        for (int c = 0; c < pst.comp_num; c++) {
+            snprintf(path, sizeof path, "%s/pan.%d", pan, c);
+            struct stat fs;
+            if (stat(path, &fs) != 0) snprintf(path, sizeof path, "%s/uniq_pan.%d", pan, c);
+            uint32_t *pcodes = slurp(path, &pb);
+            snprintf(path, sizeof path, "%s/combco.%d", in, c);
+            uint32_t *codes = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.index.%d", in, c);
+            uint64_t *index = slurp(path, &b);
+            uint32_t *oc = NULL;
+            ck(ctx, mk_set_operate(ctx, pcodes, pb / 4, codes, index, st.infile_num, op, &oc, oi), "mk_set_operate");
+            write_file(outdir, "combco", c, oc, (size_t)oi[st.infile_num] * 4);
+            write_file(outdir, "combco.index", c, oi, sizeof(uint64_t) * (size_t)(st.infile_num + 1));
+            for (int i = 0; i < st.infile_num; i++) ctx_ct[i] += (unsigned)(oi[i + 1] - oi[i]);
+            mk_free(oc); free(pcodes); free(codes); free(index);
+        }
+        write_file(outdir, "cofiles.stat", -1, stat_raw, stat_bytes);     /* (all_ctx_ct stays the input's, as in the reference) */
+    }
+    mk_ctx_destroy(ctx);
+    return 0;
+}
+
 /* ---- composite ---------------------------------------------------------------------------- */
 static const mk_species_stat *g_stats;
 static int by_hits_desc(const void *a, const void *b) { return g_stats[*(const int *)b].n - g_stats[*(const int *)a].n; }
@@ -330,12 +521,13 @@ static int cmd_composite(int argc, char **argv)
 int main(int argc, char **argv)
 {
     if (argc < 2) {
-        fprintf(stderr, "usage: %s <shuffle|dist|composite> [options] [arguments]\n", argv[0]);
+        fprintf(stderr, "usage: %s <shuffle|dist|set|composite> [options] [arguments]\n", argv[0]);
         return 1;
     }
     if (!strcmp(argv[1], "shuffle")) return cmd_shuffle(argc - 2, argv + 2);
     if (!strcmp(argv[1], "dist")) return cmd_dist(argc - 2, argv + 2);
     if (!strcmp(argv[1], "composite")) return cmd_composite(argc - 2, argv + 2);
+    if (!strcmp(argv[1], "set")) return cmd_set(argc - 2, argv + 2);
     die("sub-command outside the accelerated path", argv[1]);
     return 1;
 }

@@ -220,6 +220,21 @@ int mk_runs_merge_device(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_
 /* number of '\n' bytes in a device buffer (to derive line_base of the next shard) */
 int mk_count_newlines_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t *count);
 
+/* ---- `set -g / -q / -i`: the MarkerDB build from genome sketches, one component per call ---------------
+ * Replaces grouping_genomes() (command_set.c:831-1003), uniq_sketch_union() (:427-512) and sketch_operate()
+ * (:322-423).  All pointers are host memory; outputs are malloc'ed by the library (release with mk_free()).
+ * mk_set_group: genome g (codes[index[g] .. index[g+1])) belongs to output taxon taxon_of_genome[g] (< 0: skipped);
+ *   every taxon gets the union of its genomes' codes in the order of the reference's per-taxon hash table
+ *   (primer[LOG2(1.5 * codes) - 7] slots, 32-bit wrap-around double hashing, code 0 never stored);
+ * mk_set_uniq_union: the codes that occur exactly once in `codes`, ascending;
+ * mk_set_operate: every sketch keeps, in order, its codes that are (intersect != 0) / are not (0) in `pan`. */
+int mk_set_group(mk_ctx *ctx, const uint32_t *codes, const uint64_t *index, int n_genomes, const int32_t *taxon_of_genome,
+                 int n_taxa, uint32_t **out_codes, uint64_t *out_index /* [n_taxa + 1] */);
+int mk_set_uniq_union(mk_ctx *ctx, const uint32_t *codes, uint64_t n, uint32_t **out, uint64_t *n_out);
+int mk_set_operate(mk_ctx *ctx, const uint32_t *pan, uint64_t n_pan, const uint32_t *codes, const uint64_t *index,
+                   int n_sketches, int intersect, uint32_t **out_codes, uint64_t *out_index /* [n_sketches + 1] */);
+void mk_free(void *p);
+
 /* ---- the multi-GPU step inside the library (NCCL over NVLink; one context per rank / GPU) -------- */
 /* mk_comm_unique_id(): 128 bytes from ncclGetUniqueId() on one rank, handed to all ranks by the host's own
  * means (MPI / torch.distributed / a file); mk_comm_init() joins the communicator (ncclCommInitRank).  NCCL is

@@ -93,7 +93,7 @@ EXPORTS = [
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
     "mk_comm_unique_id", "mk_comm_init", "mk_comm_destroy", "mk_markerdb_load_sharded", "mk_fastq_koc_sharded_device",
-    "mk_fastq_koc_sharded_host",
+    "mk_fastq_koc_sharded_host", "mk_set_group", "mk_set_uniq_union", "mk_set_operate", "mk_free",
 ]
 
 _lib = None
@@ -165,6 +165,11 @@ def load():
     L.mk_synth_shuf_perm.restype = None
     L.mk_synth_shuf_id.argtypes = [u64]
     L.mk_synth_shuf_id.restype = C.c_int32
+    L.mk_set_group.argtypes = [vp, vp, vp, i32, vp, i32, C.POINTER(C.POINTER(C.c_uint32)), vp]
+    L.mk_set_uniq_union.argtypes = [vp, vp, u64, C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(u64)]
+    L.mk_set_operate.argtypes = [vp, vp, u64, vp, vp, i32, i32, C.POINTER(C.POINTER(C.c_uint32)), vp]
+    L.mk_free.argtypes = [vp]
+    L.mk_free.restype = None
     L.mk_comm_unique_id.argtypes = [vp, sz]
     L.mk_comm_init.argtypes = [vp, vp, i32, i32]
     L.mk_comm_destroy.argtypes = [vp]
@@ -474,6 +479,39 @@ class Sketcher:
         r = MkRuns()
         self._ck(self._L.mk_runs_merge_device(self._h, _ptr(d_code), _ptr(d_pos), _ptr(d_cnt), n, C.byref(r)))
         return r
+
+    # -- `set -g / -q / -i` (MarkerDB build), one component per call
+    def _take_u32(self, ptr, n: int) -> np.ndarray:
+        out = np.ctypeslib.as_array(ptr, shape=(n,)).copy() if n else np.empty(0, np.uint32)
+        self._L.mk_free(ptr)
+        return out
+
+    def set_group(self, codes, index, taxon_of_genome, n_taxa: int):
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        index = np.ascontiguousarray(index, dtype=np.uint64)
+        tax = np.ascontiguousarray(taxon_of_genome, dtype=np.int32)
+        out = C.POINTER(C.c_uint32)()
+        oi = np.zeros(n_taxa + 1, dtype=np.uint64)
+        self._ck(self._L.mk_set_group(self._h, codes.ctypes.data, index.ctypes.data, index.size - 1, tax.ctypes.data, n_taxa,
+                                      C.byref(out), oi.ctypes.data))
+        return self._take_u32(out, int(oi[-1])), oi
+
+    def set_uniq_union(self, codes) -> np.ndarray:
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        out = C.POINTER(C.c_uint32)()
+        n = C.c_uint64()
+        self._ck(self._L.mk_set_uniq_union(self._h, codes.ctypes.data, codes.size, C.byref(out), C.byref(n)))
+        return self._take_u32(out, int(n.value))
+
+    def set_operate(self, pan, codes, index, intersect: bool = True):
+        pan = np.ascontiguousarray(pan, dtype=np.uint32)
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        index = np.ascontiguousarray(index, dtype=np.uint64)
+        out = C.POINTER(C.c_uint32)()
+        oi = np.zeros(index.size, dtype=np.uint64)
+        self._ck(self._L.mk_set_operate(self._h, pan.ctypes.data, pan.size, codes.ctypes.data, index.ctypes.data, index.size - 1,
+                                        1 if intersect else 0, C.byref(out), oi.ctypes.data))
+        return self._take_u32(out, int(oi[-1])), oi
 
     # -- the multi-GPU step inside the library (NCCL; csrc/mk_comm.cu)
     @staticmethod

@@ -642,3 +642,376 @@ static int runs_finalize(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_
     if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.reduce_ms += ms;
     return rc;
 }
+
+// ================================================================================================
+// `metakssd set -g / -q / -i` on the device: the MarkerDB build from genome sketches.
+//   -g  grouping_genomes()    /root/reference/command_set.c:831-1003   union of a taxon's genome sketches
+//   -q  uniq_sketch_union()   command_set.c:427-512                    codes found in exactly one taxon
+//   -i  sketch_operate()      command_set.c:322-423 (-s: subtract)     every taxon's codes that are in the pan
+// One component per call; the host keeps the file formats and the taxon table (organize_taxf()).
+// ================================================================================================
+// 32-bit wrap-around probe of grouping_genomes() (HASH() with an unsigned int key and int table size:
+// int * unsigned -> unsigned, command_set.c:892; global_basic.h:282-284)
+__device__ __forceinline__ u32 probe_slot32(u32 code, u32 i, u32 hs)
+{
+    return (code % hs + i * (1u + code % (hs - 1u))) % hs;
+}
+
+// sequential insertion order of a taxon's table as a parallel fix point (see k_slot_assign): every slot keeps the
+// smallest rank that claimed it; here every taxon has its own table size
+__global__ void __launch_bounds__(256)
+k_set_slot_assign(const u64 *__restrict__ r_key /* taxon << 32 | code, in insertion order */, u64 n,
+                  const u32 *__restrict__ hs_taxon, u64 *__restrict__ slot_keys, u32 *__restrict__ slot_vals, u64 smask,
+                  u32 *probe_i)
+{
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    u32 carry = (u32)r;
+    u32 i = 0;
+    for (u32 guard = 0; guard < 0x7FFFFFFFu; guard++) {
+        u64 key = r_key[carry];
+        u32 taxon = (u32)(key >> 32), code = (u32)key;
+        u32 hs = hs_taxon[taxon];
+        if (i >= hs) return;                 // "hashtable overflow" in the reference: the code is not stored
+        u32 slot = probe_slot32(code, i, hs);
+        u64 skey = ((u64)taxon << 32) | slot;
+        u64 h = mix64(skey) & smask;
+        for (;;) {
+            u64 old = atomicCAS((unsigned long long *)&slot_keys[h], EMPTY64, skey);
+            if (old == EMPTY64 || old == skey) break;
+            h = (h + 1) & smask;
+        }
+        ((volatile u32 *)probe_i)[carry] = i;
+        __threadfence();
+        u32 old = atomicMin(&slot_vals[h], carry);
+        if (old == EMPTY32) break;
+        if (old > carry) {
+            __threadfence();
+            i = ((volatile u32 *)probe_i)[old] + 1;
+            carry = old;
+        } else {
+            i++;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_set_keys(const u32 *__restrict__ codes, const u32 *__restrict__ taxon_of, u64 n, u64 *__restrict__ keys, u64 *__restrict__ vals)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // code 0 reads as an empty slot in the reference's table and is never stored; taxon 0xFFFFFFFF = ignored genome
+    const bool drop = codes[i] == 0 || taxon_of[i] == 0xFFFFFFFFu;
+    keys[i] = drop ? EMPTY64 : (((u64)taxon_of[i] << 32) | codes[i]);
+    vals[i] = i;
+}
+// after a stable sort by key: the first entry of every run of equal keys survives, flagged for compaction
+__global__ void __launch_bounds__(256) k_set_first_of_run(const u64 *__restrict__ keys, u64 n, u32 *__restrict__ flag)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = keys[i] != EMPTY64 && (i == 0 || keys[i - 1] != keys[i]);
+}
+__global__ void __launch_bounds__(256)
+k_set_compact(const u64 *__restrict__ keys, const u64 *__restrict__ vals, const u32 *__restrict__ flag, const u32 *__restrict__ pos,
+              u64 n, u64 *__restrict__ o_keys /* original index */, u64 *__restrict__ o_vals /* taxon << 32 | code */)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    o_keys[pos[i]] = vals[i];
+    o_vals[pos[i]] = keys[i];
+}
+__global__ void __launch_bounds__(256)
+k_set_out_keys(const u64 *__restrict__ r_key, const u32 *__restrict__ probe_i, const u32 *__restrict__ hs_taxon, u64 n,
+               u64 *__restrict__ keys, u64 *__restrict__ vals)
+{
+    u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    u64 key = r_key[r];
+    u32 taxon = (u32)(key >> 32), code = (u32)key;
+    u32 hs = hs_taxon[taxon];
+    u32 pi = probe_i[r];
+    keys[r] = pi >= hs ? EMPTY64 : (((u64)taxon << 32) | probe_slot32(code, pi, hs));
+    vals[r] = key;
+}
+__global__ void __launch_bounds__(256)
+k_set_emit(const u64 *__restrict__ skeys, const u64 *__restrict__ svals, u64 n, u32 *__restrict__ out, u32 *__restrict__ per_taxon)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || skeys[i] == EMPTY64) return;
+    out[i] = (u32)svals[i];
+    atomicAdd(&per_taxon[(u32)(skeys[i] >> 32)], 1u);
+}
+
+// hash-table size of a taxon: primer[LOG2((ull)(total * 1.5)) - 7] (command_set.c:877-879)
+static u32 set_group_table_size(u64 total_codes)
+{
+    unsigned long long x = (unsigned long long)((double)total_codes * 1.5);
+    int lg = x ? 63 - __builtin_clzll(x) : -1;
+    // LOG2(0) in the reference is clz(0) (undefined); an empty taxon stores nothing whatever the size
+    int ind = lg > 7 ? lg - 7 : 0;
+    if (ind > 24) ind = 24;
+    // primer[i] = largest prime below 2^(8+i)
+    u64 v = (1ull << (8 + ind)) - 1;
+    for (;; v--) {
+        bool prime = v >= 2 && (v == 2 || v % 2);
+        for (u64 d = 3; prime && d * d <= v; d += 2) prime = v % d != 0;
+        if (prime) break;
+    }
+    return (u32)v;
+}
+
+extern "C" int mk_set_group(mk_ctx *ctx, const uint32_t *codes, const uint64_t *index, int n_genomes, const int32_t *taxon_of_genome,
+                            int n_taxa, uint32_t **out_codes, uint64_t *out_index)
+{
+    if (!ctx || !index || !taxon_of_genome || !out_codes || !out_index || n_genomes <= 0 || n_taxa <= 0) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *out_codes = nullptr;
+    for (int t = 0; t <= n_taxa; t++) out_index[t] = 0;
+    // insertion order of the reference: taxa in output order, a taxon's genomes in taxfile order, a genome's codes in
+    // sketch order.  The host lays the codes out in that order (genomes of one taxon are contiguous).
+    std::vector<std::vector<int>> members((size_t)n_taxa);
+    for (int g = 0; g < n_genomes; g++)
+        if (taxon_of_genome[g] >= 0 && taxon_of_genome[g] < n_taxa) members[(size_t)taxon_of_genome[g]].push_back(g);
+    u64 n = 0;
+    std::vector<u32> hs((size_t)n_taxa);
+    for (int t = 0; t < n_taxa; t++) {
+        u64 tot = 0;
+        for (int g : members[(size_t)t]) tot += index[g + 1] - index[g];
+        hs[(size_t)t] = set_group_table_size(tot);
+        n += tot;
+    }
+    if (n == 0) { *out_codes = (uint32_t *)malloc(4); return *out_codes ? MK_OK : MK_ERR_NOMEM; }
+    if (n >= 0xFFFFFFF0ull) return MK_ERR_UNSUPPORTED;
+    std::vector<u32> h_codes((size_t)n), h_tax((size_t)n);
+    {
+        u64 o = 0;
+        for (int t = 0; t < n_taxa; t++)
+            for (int g : members[(size_t)t])
+                for (u64 i = index[g]; i < index[g + 1]; i++, o++) { h_codes[(size_t)o] = codes[i]; h_tax[(size_t)o] = (u32)t; }
+    }
+    const u64 nb = (n + 255) / 256;
+    u32 *d_codes, *d_tax, *d_hs, *flag, *pos, *probe_i, *slot_vals, *d_out, *d_cnt;
+    u64 *k0, *v0, *k1, *v1, *slot_keys;
+    CKR(mk_scratch(ctx, SB_OUT_CODE, (size_t)n, &d_codes));
+    CKR(mk_scratch(ctx, SB_R_CNT, (size_t)n, &d_tax));
+    CKR(mk_scratch(ctx, SB_SEG_COUNTS, (size_t)2 * n_taxa + 2, &d_hs));
+    d_cnt = d_hs + n_taxa;
+    CKR(mk_scratch(ctx, SB_ACC_CNT, (size_t)n, &flag));
+    CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n, &pos));
+    CKR(mk_scratch(ctx, SB_R_PROBE, (size_t)n, &probe_i));
+    CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n, &k0));
+    CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n, &v0));
+    CKR(mk_scratch(ctx, SB_SORT_K1, (size_t)n, &k1));
+    CKR(mk_scratch(ctx, SB_SORT_V1, (size_t)n, &v1));
+    CK(cudaMemcpyAsync(d_codes, h_codes.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tax, h_tax.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_hs, hs.data(), (size_t)n_taxa * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d_cnt, 0, (size_t)n_taxa * 4, ctx->stream));
+    ctx->prof.h2d_bytes += n * 8;
+    // 1. first occurrence of every (taxon, code): stable sort by key, heads of runs
+    k_set_keys<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_codes, d_tax, n, k0, v0);
+    LAUNCH_COUNT(ctx);
+    int tbits = bit_length((u64)(n_taxa > 1 ? n_taxa - 1 : 1));
+    u64 *sk = k0, *sv = v0;
+    CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, 64));       // (EMPTY keys sort last: full width)
+    (void)tbits;
+    k_set_first_of_run<<<(unsigned)nb, 256, 0, ctx->stream>>>(sk, n, flag);
+    LAUNCH_COUNT(ctx);
+    u64 m = 0;
+    CKR(mk_exclusive_scan_u32(ctx, flag, pos, n, &m));
+    if (m == 0) { *out_codes = (uint32_t *)malloc(4); return *out_codes ? MK_OK : MK_ERR_NOMEM; }
+    u64 *ok = sk == k0 ? k1 : k0, *ov = sv == v0 ? v1 : v0;          // the other pair of buffers
+    k_set_compact<<<(unsigned)nb, 256, 0, ctx->stream>>>(sk, sv, flag, pos, n, ok, ov);
+    LAUNCH_COUNT(ctx);
+    // 2. insertion order = original index order
+    u64 *rk = ok, *rv = ov;
+    CKR(mk_radix_sort_pairs(ctx, &rk, &rv, rk == k0 ? k1 : k0, rv == v0 ? v1 : v0, m, 0, bit_length(n)));
+    // rv = taxon << 32 | code in insertion order
+    // 3. slot of every code in its taxon's table
+    const u64 mb = (m + 255) / 256;
+    u64 scap = pow2_at_least(2 * m + 2);
+    CKR(mk_scratch(ctx, SB_SLOT_KEYS, (size_t)scap, &slot_keys));
+    CKR(mk_scratch(ctx, SB_SLOT_VALS, (size_t)scap, &slot_vals));
+    CK(cudaMemsetAsync(slot_keys, 0xFF, (size_t)scap * 8, ctx->stream));
+    CK(cudaMemsetAsync(slot_vals, 0xFF, (size_t)scap * 4, ctx->stream));
+    CK(cudaMemsetAsync(probe_i, 0xFF, (size_t)m * 4, ctx->stream));
+    k_set_slot_assign<<<(unsigned)mb, 256, 0, ctx->stream>>>(rv, m, d_hs, slot_keys, slot_vals, scap - 1, probe_i);
+    LAUNCH_COUNT(ctx);
+    // 4. order by (taxon, slot)
+    u64 *fk = rk, *fv = rk == k0 ? k1 : k0;       // reuse: keys into the buffer rk, values into its twin
+    u64 *src_keys = rv;
+    // (rk holds original indices, no longer needed; rv must stay readable while the out keys are built)
+    u64 *alt_k = (fk == k0) ? k1 : k0;
+    (void)alt_k;
+    u64 *tmp_vals = (rv == v0) ? v1 : v0;
+    k_set_out_keys<<<(unsigned)mb, 256, 0, ctx->stream>>>(src_keys, probe_i, d_hs, m, fk, tmp_vals);
+    LAUNCH_COUNT(ctx);
+    u64 *ek = fk, *ev = tmp_vals;
+    CKR(mk_radix_sort_pairs(ctx, &ek, &ev, fv, rv, m, 0, 64));
+    CKR(mk_scratch(ctx, SB_OUT_CODE, (size_t)n, &d_out));
+    k_set_emit<<<(unsigned)mb, 256, 0, ctx->stream>>>(ek, ev, m, d_out, d_cnt);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+    std::vector<u32> cnt((size_t)n_taxa);
+    CK(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)n_taxa * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    u64 total = 0;
+    for (int t = 0; t < n_taxa; t++) { out_index[t] = total; total += cnt[(size_t)t]; }
+    out_index[n_taxa] = total;
+    *out_codes = (uint32_t *)malloc((size_t)(total ? total : 1) * 4);
+    if (!*out_codes) return MK_ERR_NOMEM;
+    CK(cudaMemcpy(*out_codes, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost));     // (stored codes sort before dropped ones)
+    ctx->prof.d2h_bytes += total * 4;
+    return MK_OK;
+}
+
+// ---- -q: codes that occur exactly once in the pan (ascending, like the reference's bitmap scan) ----------
+__global__ void __launch_bounds__(256) k_set_u32_keys(const u32 *__restrict__ codes, u64 n, u64 *__restrict__ keys, u64 *__restrict__ vals)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { keys[i] = codes[i]; vals[i] = i; }
+}
+__global__ void __launch_bounds__(256) k_set_single(const u64 *__restrict__ keys, u64 n, u32 *__restrict__ flag)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flag[i] = (i == 0 || keys[i - 1] != keys[i]) && (i + 1 == n || keys[i + 1] != keys[i]);
+}
+__global__ void __launch_bounds__(256)
+k_set_take_u32(const u64 *__restrict__ keys, const u32 *__restrict__ flag, const u32 *__restrict__ pos, u64 n, u32 *__restrict__ out)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = (u32)keys[i];
+}
+
+extern "C" int mk_set_uniq_union(mk_ctx *ctx, const uint32_t *codes, uint64_t n, uint32_t **out, uint64_t *n_out)
+{
+    if (!ctx || !out || !n_out || (!codes && n)) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    *n_out = 0;
+    *out = (uint32_t *)malloc((size_t)(n ? n : 1) * 4);
+    if (!*out) return MK_ERR_NOMEM;
+    if (n == 0) return MK_OK;
+    if (n >= 0xFFFFFFF0ull) return MK_ERR_UNSUPPORTED;
+    const u64 nb = (n + 255) / 256;
+    u32 *d_codes, *flag, *pos, *d_out;
+    u64 *k0, *v0, *k1, *v1;
+    CKR(mk_scratch(ctx, SB_OUT_CODE, (size_t)n, &d_codes));
+    CKR(mk_scratch(ctx, SB_ACC_CNT, (size_t)n, &flag));
+    CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n, &pos));
+    CKR(mk_scratch(ctx, SB_R_CNT, (size_t)n, &d_out));
+    CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n, &k0));
+    CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n, &v0));
+    CKR(mk_scratch(ctx, SB_SORT_K1, (size_t)n, &k1));
+    CKR(mk_scratch(ctx, SB_SORT_V1, (size_t)n, &v1));
+    CK(cudaMemcpyAsync(d_codes, codes, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof.h2d_bytes += n * 4;
+    k_set_u32_keys<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_codes, n, k0, v0);
+    LAUNCH_COUNT(ctx);
+    u64 *sk = k0, *sv = v0;
+    CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, 32));
+    k_set_single<<<(unsigned)nb, 256, 0, ctx->stream>>>(sk, n, flag);
+    LAUNCH_COUNT(ctx);
+    u64 m = 0;
+    CKR(mk_exclusive_scan_u32(ctx, flag, pos, n, &m));
+    k_set_take_u32<<<(unsigned)nb, 256, 0, ctx->stream>>>(sk, flag, pos, n, d_out);
+    LAUNCH_COUNT(ctx);
+    CK(cudaMemcpyAsync(*out, d_out, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.d2h_bytes += m * 4;
+    *n_out = m;
+    return MK_OK;
+}
+
+// ---- -i / -s: keep every sketch's codes that are (intersect = 1) / are not (0) in the pan, order kept -------
+__global__ void __launch_bounds__(256)
+k_set_member(const u32 *__restrict__ codes, u64 n, const u32 *__restrict__ pan_sorted, u64 n_pan, int intersect, u32 *__restrict__ flag)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 c = codes[i];
+    u64 a = 0, b = n_pan;
+    while (a < b) { u64 m = (a + b) >> 1; if (pan_sorted[m] < c) a = m + 1; else b = m; }
+    const bool in = a < n_pan && pan_sorted[a] == c;
+    flag[i] = in == (intersect != 0);
+}
+__global__ void __launch_bounds__(256)
+k_set_take_codes(const u32 *__restrict__ codes, const u32 *__restrict__ flag, const u32 *__restrict__ pos, u64 n, u32 *__restrict__ out)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && flag[i]) out[pos[i]] = codes[i];
+}
+__global__ void k_set_index(const u32 *__restrict__ pos, const u32 *__restrict__ flag, const u64 *__restrict__ index, int n_sketches, u64 n, u64 *__restrict__ out_index)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > n_sketches) return;
+    const u64 i = index[s];
+    out_index[s] = i < n ? pos[i] : (n ? pos[n - 1] + flag[n - 1] : 0);
+}
+
+__global__ void k_set_narrow(const u64 *__restrict__ k, u64 n, u32 *__restrict__ o);
+
+extern "C" int mk_set_operate(mk_ctx *ctx, const uint32_t *pan, uint64_t n_pan, const uint32_t *codes, const uint64_t *index,
+                              int n_sketches, int intersect, uint32_t **out_codes, uint64_t *out_index)
+{
+    if (!ctx || !index || !out_codes || !out_index || n_sketches <= 0 || (!pan && n_pan)) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const u64 n = index[n_sketches];
+    *out_codes = (uint32_t *)malloc((size_t)(n ? n : 1) * 4);
+    if (!*out_codes) return MK_ERR_NOMEM;
+    for (int s = 0; s <= n_sketches; s++) out_index[s] = 0;
+    if (n == 0) return MK_OK;
+    if (n >= 0xFFFFFFF0ull || n_pan >= 0xFFFFFFF0ull) return MK_ERR_UNSUPPORTED;
+    const u64 nb = (n + 255) / 256;
+    u32 *d_codes, *d_pan, *flag, *pos, *d_out;
+    u64 *k0, *v0, *k1, *v1, *d_index, *d_oindex;
+    CKR(mk_scratch(ctx, SB_OUT_CODE, (size_t)n, &d_codes));
+    CKR(mk_scratch(ctx, SB_R_PROBE, (size_t)(n_pan ? n_pan : 1), &d_pan));
+    CKR(mk_scratch(ctx, SB_ACC_CNT, (size_t)n, &flag));
+    CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n, &pos));
+    CKR(mk_scratch(ctx, SB_R_CNT, (size_t)n, &d_out));
+    CKR(mk_scratch(ctx, SB_FILE_OFF, (size_t)2 * (n_sketches + 1), &d_index));
+    d_oindex = d_index + n_sketches + 1;
+    CK(cudaMemcpyAsync(d_codes, codes, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_index, index, (size_t)(n_sketches + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof.h2d_bytes += n * 4 + n_pan * 4;
+    if (n_pan) {      // the pan as a sorted array (uniq_pan files are ascending already; pan files of -g are not)
+        CKR(mk_scratch(ctx, SB_SORT_K0, (size_t)n_pan, &k0));
+        CKR(mk_scratch(ctx, SB_SORT_V0, (size_t)n_pan, &v0));
+        CKR(mk_scratch(ctx, SB_SORT_K1, (size_t)n_pan, &k1));
+        CKR(mk_scratch(ctx, SB_SORT_V1, (size_t)n_pan, &v1));
+        u32 *tmp;
+        CKR(mk_scratch(ctx, SB_X_QCODE, (size_t)n_pan, &tmp));
+        CK(cudaMemcpyAsync(tmp, pan, (size_t)n_pan * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const u64 pb = (n_pan + 255) / 256;
+        k_set_u32_keys<<<(unsigned)pb, 256, 0, ctx->stream>>>(tmp, n_pan, k0, v0);
+        LAUNCH_COUNT(ctx);
+        u64 *sk = k0, *sv = v0;
+        CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n_pan, 0, 32));
+        k_set_narrow<<<(unsigned)pb, 256, 0, ctx->stream>>>(sk, n_pan, d_pan);
+        LAUNCH_COUNT(ctx);
+    }
+    k_set_member<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_codes, n, d_pan, n_pan, intersect, flag);
+    LAUNCH_COUNT(ctx);
+    u64 m = 0;
+    CKR(mk_exclusive_scan_u32(ctx, flag, pos, n, &m));
+    k_set_take_codes<<<(unsigned)nb, 256, 0, ctx->stream>>>(d_codes, flag, pos, n, d_out);
+    LAUNCH_COUNT(ctx);
+    k_set_index<<<(n_sketches + 256) / 256, 256, 0, ctx->stream>>>(pos, flag, d_index, n_sketches, n, d_oindex);
+    LAUNCH_COUNT(ctx);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(*out_codes, d_out, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out_index, d_oindex, (size_t)(n_sketches + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.d2h_bytes += m * 4;
+    return MK_OK;
+}
+
+__global__ void k_set_narrow(const u64 *__restrict__ k, u64 n, u32 *__restrict__ o)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = (u32)k[i];
+}
+
+extern "C" void mk_free(void *p) { free(p); }

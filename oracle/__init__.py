@@ -71,6 +71,14 @@ def lib():
         L.ko_fastq_co.restype = C.POINTER(KoSketch)
         L.ko_fasta_co_uniq.argtypes = [C.POINTER(KoParams), C.c_void_p, C.c_void_p, C.c_size_t]
         L.ko_fasta_co_uniq.restype = C.POINTER(KoSketch)
+        L.ko_organize_taxa.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ko_organize_taxa.restype = C.c_int
+        L.ko_set_group.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.ko_set_group.restype = None
+        L.ko_set_uniq_union.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.ko_set_uniq_union.restype = C.c_size_t
+        L.ko_set_operate.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ko_set_operate.restype = None
         L.ko_sketch_free.argtypes = [C.POINTER(KoSketch)]
         L.ko_composite_component.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
@@ -214,6 +222,44 @@ def fasta_co_uniq(p: KoParams, perm: np.ndarray, text) -> Sketch:
     """`dist -u` on FASTA: uniq_fasta2co() (iseq2comem.c:729-828), codes occurring once in the file."""
     t = _as_bytes(text)
     return _take(lib().ko_fasta_co_uniq(C.byref(p), perm.ctypes.data, t.ctypes.data, t.size), False)
+
+
+# --------------------------------------------------------------------------- set -g / -q / -i
+def organize_taxa(taxids):
+    """organize_taxf(): (taxon_of_genome int32[], taxid_of_taxon list) in the reference's output order."""
+    tid = np.ascontiguousarray(taxids, dtype=np.int32)
+    taxon_of = np.empty(tid.size, dtype=np.int32)
+    ids = np.empty(tid.size, dtype=np.int32)
+    n = lib().ko_organize_taxa(tid.ctypes.data, tid.size, taxon_of.ctypes.data, ids.ctypes.data)
+    return taxon_of, ids[:n].tolist()
+
+
+def set_group(codes, index, taxon_of, n_taxa):
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    index = np.ascontiguousarray(index, dtype=np.uint64)
+    taxon_of = np.ascontiguousarray(taxon_of, dtype=np.int32)
+    out = np.empty(max(1, codes.size), dtype=np.uint32)
+    oi = np.zeros(n_taxa + 1, dtype=np.uint64)
+    lib().ko_set_group(codes.ctypes.data, index.ctypes.data, index.size - 1, taxon_of.ctypes.data, n_taxa, out.ctypes.data, oi.ctypes.data)
+    return out[:int(oi[-1])].copy(), oi
+
+
+def set_uniq_union(codes):
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    out = np.empty(max(1, codes.size), dtype=np.uint32)
+    n = lib().ko_set_uniq_union(codes.ctypes.data, codes.size, out.ctypes.data)
+    return out[:n].copy()
+
+
+def set_operate(pan, codes, index, intersect=True):
+    pan = np.ascontiguousarray(pan, dtype=np.uint32)
+    codes = np.ascontiguousarray(codes, dtype=np.uint32)
+    index = np.ascontiguousarray(index, dtype=np.uint64)
+    out = np.empty(max(1, codes.size), dtype=np.uint32)
+    oi = np.zeros(index.size, dtype=np.uint64)
+    lib().ko_set_operate(pan.ctypes.data, pan.size, codes.ctypes.data, index.ctypes.data, index.size - 1, 1 if intersect else 0,
+                         out.ctypes.data, oi.ctypes.data)
+    return out[:int(oi[-1])].copy(), oi
 
 
 # --------------------------------------------------------------------------- composite

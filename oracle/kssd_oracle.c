@@ -458,6 +458,107 @@ void ko_split_components(const ko_params *p, const ko_sketch *s, uint32_t *comp_
     }
 }
 
+/* ---------------- `set -g / -q / -i`: the MarkerDB pipeline (command_set.c) ------------------------------
+ * ko_organize_taxa: organize_taxf() (command_set.c:635-704) — taxa live in an open-addressing table of
+ * nextPrime((int)(lines / 0.6)) slots probed with HASH(taxid, n, size) in int arithmetic; the output order of the
+ * taxa is ascending slot.  taxon_of[g] receives the output position of genome g's taxon (or -1 for taxid 0, which
+ * grouping_genomes() skips; its position is still counted).  Returns the number of taxa including a taxid-0 one. */
+static int next_prime_int(int n);
+int ko_organize_taxa(const int *taxid, int n_genomes, int *taxon_of, int *taxid_of_taxon)
+{
+    int hashsz = next_prime_int((int)((double)n_genomes / 0.6));
+    int *tab = (int *)malloc(sizeof(int) * (size_t)(hashsz > 0 ? hashsz : 1));
+    for (int i = 0; i < hashsz; i++) tab[i] = -1;
+    int *slot_of = (int *)malloc(sizeof(int) * (size_t)n_genomes);
+    for (int g = 0; g < n_genomes; g++) {
+        slot_of[g] = -1;
+        for (int n = 0; n < hashsz; n++) {
+            int hv = (taxid[g] % hashsz + n * (1 + taxid[g] % (hashsz - 1))) % hashsz;
+            if (tab[hv] == -1) { tab[hv] = taxid[g]; slot_of[g] = hv; break; }
+            if (tab[hv] == taxid[g]) { slot_of[g] = hv; break; }
+        }
+    }
+    int n_taxa = 0;
+    int *pos_of_slot = (int *)malloc(sizeof(int) * (size_t)(hashsz > 0 ? hashsz : 1));
+    for (int i = 0; i < hashsz; i++) {
+        pos_of_slot[i] = -1;
+        if (tab[i] != -1) { taxid_of_taxon[n_taxa] = tab[i]; pos_of_slot[i] = n_taxa++; }
+    }
+    for (int g = 0; g < n_genomes; g++) taxon_of[g] = slot_of[g] < 0 ? -1 : pos_of_slot[slot_of[g]];
+    free(tab); free(slot_of); free(pos_of_slot);
+    return n_taxa;
+}
+
+/* grouping_genomes() (command_set.c:831-1003), one component: per taxon an open-addressing table of
+ * primer[LOG2((ull)(codes * 1.5)) - 7] slots (primer[0] below 2^8), HASH() in 32-bit wrap-around arithmetic,
+ * 0 = empty (so code 0 is never stored); genomes in taxfile order, codes in sketch order; written in ascending
+ * slot order.  taxon_of[g] < 0 skips the genome.  out_codes needs room for index[n_genomes] values. */
+void ko_set_group(const uint32_t *codes, const size_t *index, int n_genomes, const int *taxon_of, int n_taxa,
+                  uint32_t *out_codes, size_t *out_index)
+{
+    size_t o = 0;
+    out_index[0] = 0;
+    for (int t = 0; t < n_taxa; t++) {
+        size_t total = 0;
+        for (int g = 0; g < n_genomes; g++)
+            if (taxon_of[g] == t) total += index[g + 1] - index[g];
+        unsigned long long x = (unsigned long long)((double)total * 1.5);
+        int lg = x ? 63 - __builtin_clzll(x) : -1;
+        int ind = lg > 7 ? lg - 7 : 0;
+        unsigned hs = prime_below_pow2(8 + ind);
+        uint32_t *tab = (uint32_t *)calloc(hs, sizeof(uint32_t));
+        for (int g = 0; g < n_genomes; g++) {
+            if (taxon_of[g] != t) continue;
+            for (size_t i = index[g]; i < index[g + 1]; i++) {
+                unsigned key = codes[i];
+                for (int xx = 0; xx < (int)hs; xx++) {
+                    unsigned y = (key % hs + (unsigned)xx * (1u + key % (hs - 1u))) % hs;
+                    if (tab[y] == 0) { tab[y] = key; break; }
+                    if (tab[y] == key) break;
+                }
+            }
+        }
+        for (unsigned y = 0; y < hs; y++)
+            if (tab[y] != 0) out_codes[o++] = tab[y];
+        out_index[t + 1] = o;
+        free(tab);
+    }
+}
+
+/* uniq_sketch_union() (command_set.c:427-512): codes that occur exactly once in the whole pan, ascending */
+static int cmp_u32v(const void *a, const void *b) { uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b; return x < y ? -1 : x > y; }
+size_t ko_set_uniq_union(const uint32_t *codes, size_t n, uint32_t *out)
+{
+    uint32_t *s = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+    memcpy(s, codes, sizeof(uint32_t) * n);
+    qsort(s, n, sizeof(uint32_t), cmp_u32v);
+    size_t m = 0;
+    for (size_t i = 0; i < n; i++)
+        if ((i == 0 || s[i - 1] != s[i]) && (i + 1 == n || s[i + 1] != s[i])) out[m++] = s[i];
+    free(s);
+    return m;
+}
+
+/* sketch_operate() (command_set.c:322-423): every sketch keeps the codes that are (intersect) / are not (subtract)
+ * in the pan, order kept */
+void ko_set_operate(const uint32_t *pan, size_t n_pan, const uint32_t *codes, const size_t *index, int n_sketches,
+                    int intersect, uint32_t *out_codes, size_t *out_index)
+{
+    uint32_t *s = (uint32_t *)malloc(sizeof(uint32_t) * (n_pan ? n_pan : 1));
+    memcpy(s, pan, sizeof(uint32_t) * n_pan);
+    qsort(s, n_pan, sizeof(uint32_t), cmp_u32v);
+    size_t o = 0;
+    out_index[0] = 0;
+    for (int k = 0; k < n_sketches; k++) {
+        for (size_t i = index[k]; i < index[k + 1]; i++) {
+            int in = bsearch(&codes[i], s, n_pan, sizeof(uint32_t), cmp_u32v) != NULL;
+            if (in == (intersect != 0)) out_codes[o++] = codes[i];
+        }
+        out_index[k + 1] = o;
+    }
+    free(s);
+}
+
 /* ---------------- composite -------------------------------------------------------------- */
 /* global_basic.c:453-475 (nextPrime): smallest prime >= n by trial division up to (int)sqrt(n) */
 static int next_prime_int(int n)

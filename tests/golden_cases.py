@@ -133,3 +133,26 @@ def uniq_cases():
         yield "uniq_sp%d" % s, (11, 6, 3, 1234), g + b">copy\n" + body[: len(body) * (s + 1) // 4]
     yield "uniq_plain", (11, 6, 3, 1234), bytes(S.fasta(4))
     yield "uniq_l2k11", (11, 5, 2, 2234), bytes(S.fasta(5)) + b">c\n" + bytes(S.fasta(5)).split(b"\n", 1)[1][:40_000]
+
+
+def set_case():
+    """((k, subk, L, shuf_seed), genome texts, "taxid\\tname" lines) for `set -g / -q / -i`: 10 species with 1-4
+    strains each (1 % substitutions), taxids that do not hash in input order, members of a species not adjacent."""
+    S = O.synth(79, 10, 180_000, 150)
+    rng = np.random.default_rng(11)
+    taxids = [562, 1280, 1351, 287, 1313, 9606, 10090, 1773, 632, 727]
+    n_strains = [3, 1, 4, 2, 3, 1, 2, 4, 3, 2]
+    genomes, groups = [], []
+    for s in range(10):
+        g = np.frombuffer(bytes(S.fasta(s)), dtype=np.uint8).copy()
+        hdr_end = int(np.flatnonzero(g == 10)[0]) + 1
+        for st in range(n_strains[s]):
+            t = g.copy()
+            if st:
+                idx = rng.integers(hdr_end, t.size, size=t.size // 100)
+                idx = idx[t[idx] != 10]
+                t[idx] = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=idx.size)]
+            genomes.append(t.tobytes())
+            groups.append("%d\tsp%d" % (taxids[s], s))
+    order = rng.permutation(len(genomes))
+    return (11, 6, 3, 1234), [genomes[i] for i in order], [groups[i] for i in order]

@@ -46,3 +46,33 @@ def test_fasta_uniq_golden(oracle, gold):
             assert sk.codes.size < oracle.fasta_co(p, perm, text).codes.size
         n += 1
     assert n >= 5
+
+
+def _set_inputs(oracle, gold):
+    (k, subk, L, seed), genomes, groups = G.set_case()
+    sid, perm = oracle.make_shuf(seed, k, subk, L)
+    p = oracle.params(k, subk, L)
+    order = [int(x) for x in gold["set/gsk_order"]]          # the reference lists genomes in a time-seeded order
+    sk = [oracle.fasta_co(p, perm, genomes[g]).components(p)[0][0] for g in order]
+    codes = np.concatenate(sk)
+    index = np.zeros(len(sk) + 1, np.uint64)
+    index[1:] = np.cumsum([s.size for s in sk])
+    taxids = [int(groups[g].split("\t")[0]) for g in order]
+    names = {int(groups[g].split("\t")[0]): groups[g].split("\t")[1] for g in order}
+    return codes, index, taxids, names
+
+
+def test_set_pipeline_golden(oracle, gold):
+    """organize_taxf() order, grouping_genomes(), uniq_sketch_union(), sketch_operate() against the reference's
+    pan / union_sp / markerdb directories"""
+    codes, index, taxids, names = _set_inputs(oracle, gold)
+    taxon_of, ids = oracle.organize_taxa(taxids)
+    assert ["%d_%s" % (t, names[t]) for t in ids] == [str(x) for x in gold["set/pan/names"]]
+    pc, pi = oracle.set_group(codes, index, taxon_of, len(ids))
+    assert np.array_equal(pc, gold["set/pan/combco.0"]) and np.array_equal(pi, gold["set/pan/index.0"])
+    u = oracle.set_uniq_union(pc)
+    assert np.array_equal(u, gold["set/uniq_pan.0"]) and 0 < u.size < pc.size
+    mc, mi = oracle.set_operate(u, pc, pi, True)
+    assert np.array_equal(mc, gold["set/markerdb/combco.0"]) and np.array_equal(mi, gold["set/markerdb/index.0"])
+    sc, si = oracle.set_operate(u, pc, pi, False)
+    assert sc.size + mc.size == pc.size

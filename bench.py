@@ -773,7 +773,8 @@ def cpu_baseline(args, sk, spec, shuf_id, perm, mdb, d_text, composite):
 
 def _markerdb_subset_parity(args, sk, spec, shuf_path, workdir, threads, n_sub=40):
     """MarkerDB of the first n_sub species built by the reference's own pipeline (dist -> set -g -> set -q -> set -i,
-    command_set.c:831,427,322) against the one the GPU path builds from the same genomes."""
+    command_set.c:831,427,322) against the one the device pipeline (FASTA sketches, mk_set_group / mk_set_uniq_union /
+    mk_set_operate) builds from the same genomes: same species order, same code order, same offsets."""
     import torch
     import oracle as O
     from metakssd_b200 import workload as W
@@ -792,14 +793,14 @@ def _markerdb_subset_parity(args, sk, spec, shuf_path, workdir, threads, n_sub=4
     os.makedirs(os.path.join(workdir, "refmdb"), exist_ok=True)
     mdb_ref = O.ref_build_markerdb(shuf_path, paths, groups, os.path.join(workdir, "refmdb"), p=threads)
     md = O.read_sketch_dir(mdb_ref)
-    ours = W.markerdb_from_species_sketches(sk.fasta_co_device(buf, off), sk.info.component_num)
-    ok = md.infile_num == n_sub
-    for i, nme in enumerate(md.names):
-        s = int(nme.split("_sp")[1])
-        for c in range(md.comp_num):
-            a = np.sort(md.combco[c][int(md.index[c][i]):int(md.index[c][i + 1])])
-            b = np.sort(ours[c][0][int(ours[c][1][s]):int(ours[c][1][s + 1])])
-            ok = ok and np.array_equal(a, b)
+    # the same genome sketches in the order the reference's `dist` listed them, through the device pipeline
+    gsk = O.read_sketch_dir(os.path.join(workdir, "refmdb", "gsk"))
+    order = [int(os.path.basename(nme)[2:].split(".")[0]) for nme in gsk.names]
+    sks = sk.fasta_co_device(buf, off)
+    ours = W.markerdb_pipeline(sk, [sks[g] for g in order], [g + 1 for g in order], ["sp%d" % g for g in order])
+    ok = md.infile_num == n_sub and ours.names == md.names
+    for c in range(md.comp_num):            # byte for byte: species order, code order inside a species, offsets
+        ok = ok and np.array_equal(ours.comp[c][0], md.combco[c]) and np.array_equal(ours.comp[c][1], md.index[c])
     shutil.rmtree(gdir, ignore_errors=True)
     return {"markerdb_subset_vs_reference_set_pipeline": {"ok": bool(ok), "species": n_sub,
                                                           "codes": int(sum(c.size for c in md.combco))}}

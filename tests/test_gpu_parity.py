@@ -253,12 +253,24 @@ def test_composite_multi_component(oracle, lib_built, shuf):
     assert composite_tsv("q.fq", names, stats_res) == want
 
 
-def test_empty_query_is_an_error(sk311, lib_built):
+def test_empty_and_one_code_query_components(sk311, lib_built, oracle):
+    """command_composite.c:535: a query component with NO code gets a dictionary of 0 slots — both loops run zero
+    times, no hit, no error (a 16-component sketch of a shallow sample has such components); with exactly ONE code
+    the table has 1 slot and HASH() divides by zero: the reference dies, the library reports MK_ERR_EMPTY_QUERY."""
     s, perm, p = sk311
     ref = (np.arange(100, dtype=np.uint32), np.array([0, 50, 100], dtype=np.uint64))
+    stats = s.composite([ref], [(np.empty(0, np.uint32), np.empty(0, np.uint16))])
+    assert int(stats["n"].sum()) == 0
+    assert oracle.composite([ref], ["a", "b"], [(np.empty(0, np.uint32), np.empty(0, np.uint16))], "q") == ""
+    # an empty component next to a populated one: the populated one still counts
+    qc = np.arange(10, 60, dtype=np.uint32)
+    stats = s.composite([ref, ref], [(np.empty(0, np.uint32), np.empty(0, np.uint16)), (qc, np.full(50, 3, np.uint16))])
+    assert stats["n"].tolist() == [40, 10]
     with pytest.raises(lib_built.MkError) as ei:
-        s.composite([ref], [(np.empty(0, np.uint32), np.empty(0, np.uint16))])
+        s.composite([ref], [(np.array([5], np.uint32), np.array([1], np.uint16))])
     assert ei.value.code == -8
+    with pytest.raises(ValueError):
+        oracle.composite([ref], ["a", "b"], [(np.array([5], np.uint32), np.array([1], np.uint16))], "q")
 
 
 def test_host_upload_pipeline_chunks(oracle, sk311, monkeypatch):

@@ -99,17 +99,19 @@ def test_composite_tsv_matches_reference_printf(oracle, lib_built):
     assert got == want and want.count("\n") > 40
 
 
-def test_markerdb_semantics(lib_built):
-    from helpers import markerdb_from_sketches
-    from metakssd_b200.workload import markerdb_from_species_sketches
+def test_organize_taxa_matches_oracle(lib_built, oracle):
+    """workload.organize_taxa (host logic of the MarkerDB pipeline) lists the taxa like organize_taxf()
+    (command_set.c:635-704), here against the oracle's restatement (itself pinned to the reference binary)"""
+    from metakssd_b200.workload import organize_taxa
     rng = np.random.default_rng(3)
-    sk = [lib_built.Sketch([rng.choice(5000, size=400, replace=False).astype(np.uint32)], None) for _ in range(12)]
-    (codes, index), = markerdb_from_species_sketches(sk, 1)
-    c2, i2 = markerdb_from_sketches([s.codes[0] for s in sk])
-    assert np.array_equal(codes, c2) and np.array_equal(index, i2)
-    allc = np.concatenate([s.codes[0] for s in sk])
-    u, n = np.unique(allc, return_counts=True)
-    assert set(codes.tolist()) == set(u[n == 1].tolist())
+    for n in (2, 7, 100, 1000):          # (a one-line taxfile divides by zero in the reference: hash size 1)
+        taxids = rng.integers(1, 3_000_000, size=n).tolist()
+        taxids += taxids[: n // 3]                       # several genomes per taxon
+        a, ids_a = organize_taxa(taxids)
+        b, ids_b = oracle.organize_taxa(taxids)
+        assert ids_a == ids_b and np.array_equal(a, b)
+    a, ids = organize_taxa([s + 1 for s in range(1000)])
+    assert sorted(ids) == list(range(1, 1001))
 
 
 def test_c_coverage_formatter_matches_python(lib_built):

@@ -78,6 +78,8 @@ typedef struct mk_sketch {
     uint64_t *n;
     uint32_t **codes;
     uint16_t **counts;
+    int borrowed;            /* 1: codes[c] / counts[c] point into the context's pinned staging block (valid until the
+                                next call on the context; mk_ctx_set_borrowed_output), mk_sketch_free() leaves them */
 } mk_sketch;
 
 /* Accumulated device timings (CUDA events on the context's stream), for bench/roofline. */
@@ -144,6 +146,10 @@ int mk_fasta_co_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sket
 int mk_fasta_co_files(mk_ctx *ctx, const char *const *paths, int n_files, const char *pipecmd, mk_sketch *out);
 
 void mk_sketch_free(mk_sketch *s);
+/* on: the sketches of the following calls are not copied out of the pinned block the results arrive in (no
+ * per-component malloc + memcpy): what a caller wants that writes the arrays straight to files or only needs the
+ * resident copy for mk_composite_component_last(). */
+int mk_ctx_set_borrowed_output(mk_ctx *ctx, int on);
 
 /* ---- composite --------------------------------------------------------------------------- */
 /* One (query, component) step of get_species_abundance(): for every species s and every

@@ -51,6 +51,7 @@ class MkSketch(C.Structure):
     _fields_ = [
         ("n_components", C.c_int), ("n_total", C.c_uint64), ("n", C.POINTER(C.c_uint64)),
         ("codes", C.POINTER(C.POINTER(C.c_uint32))), ("counts", C.POINTER(C.POINTER(C.c_uint16))),
+        ("borrowed", C.c_int),
     ]
 
 
@@ -85,7 +86,7 @@ EXPORTS = [
     "mk_strerror", "mk_last_error", "mk_device_count", "mk_ctx_create", "mk_ctx_destroy", "mk_ctx_info",
     "mk_ctx_profile", "mk_ctx_synchronize", "mk_ctx_cuda_stream", "mk_fastq_koc_device", "mk_fastq_koc_host", "mk_fastq_koc_file",
     "mk_fasta_co_device", "mk_fasta_co_host", "mk_fasta_co_file", "mk_fasta_co_files", "mk_fastq_co_device",
-    "mk_fastq_co_host", "mk_fastq_co_file", "mk_ctx_set_dedup", "mk_sketch_free", "mk_composite_begin",
+    "mk_fastq_co_host", "mk_fastq_co_file", "mk_ctx_set_dedup", "mk_ctx_set_borrowed_output", "mk_sketch_free", "mk_composite_begin",
     "mk_composite_component", "mk_composite_stats", "mk_composite_hits", "mk_markerdb_load", "mk_markerdb_unload",
     "mk_composite_component_resident", "mk_composite_component_last", "mk_format_species_coverage",
     "mk_fastq_partial_device", "mk_fastq_partial_host",
@@ -133,6 +134,7 @@ def load():
     L.mk_fastq_co_host.argtypes = [vp, vp, sz, i32, i32, C.POINTER(MkSketch)]
     L.mk_fastq_co_file.argtypes = [vp, C.c_char_p, C.c_char_p, i32, i32, C.POINTER(MkSketch)]
     L.mk_ctx_set_dedup.argtypes = [vp, i32]
+    L.mk_ctx_set_borrowed_output.argtypes = [vp, i32]
     L.mk_sketch_free.argtypes = [C.POINTER(MkSketch)]
     L.mk_sketch_free.restype = None
     L.mk_composite_begin.argtypes = [vp, i32]
@@ -253,12 +255,17 @@ class Sketch:
 
 
 def _take_sketch(sk: MkSketch, with_counts: bool) -> Sketch:
+    """numpy arrays of a returned sketch.  A borrowed sketch (Sketcher.set_borrowed_output) is NOT copied: its arrays
+    are views of the context's pinned staging block, valid until the next call on that context."""
     codes, counts = [], ([] if with_counts else None)
+    borrowed = bool(sk.borrowed)
     for c in range(sk.n_components):
         n = int(sk.n[c])
-        codes.append(np.ctypeslib.as_array(sk.codes[c], shape=(n,)).copy() if n else np.empty(0, np.uint32))
+        a = np.ctypeslib.as_array(sk.codes[c], shape=(n,)) if n else np.empty(0, np.uint32)
+        codes.append(a if borrowed or not n else a.copy())
         if with_counts:
-            counts.append(np.ctypeslib.as_array(sk.counts[c], shape=(n,)).copy() if n else np.empty(0, np.uint16))
+            b = np.ctypeslib.as_array(sk.counts[c], shape=(n,)) if n else np.empty(0, np.uint16)
+            counts.append(b if borrowed or not n else b.copy())
     load().mk_sketch_free(C.byref(sk))
     return Sketch(codes, counts)
 
@@ -360,6 +367,10 @@ class Sketcher:
         sk = MkSketch()
         self._ck(self._L.mk_fastq_co_file(self._h, path.encode(), pipecmd.encode(), quality, min_occurrence, C.byref(sk)))
         return _take_sketch(sk, False)
+
+    def set_borrowed_output(self, on: bool):
+        """Sketches of the following calls come back as views into the pinned staging block (no host copies)."""
+        self._ck(self._L.mk_ctx_set_borrowed_output(self._h, 1 if on else 0))
 
     def set_dedup(self, on: bool):
         """`dist -u`: the following fasta_co_* calls keep only codes that occur once in their genome."""

@@ -240,7 +240,7 @@ extern "C" void *mk_ctx_cuda_stream(mk_ctx *ctx) { return ctx ? (void *)ctx->str
 extern "C" void mk_sketch_free(mk_sketch *s)
 {
     if (!s) return;
-    for (int c = 0; c < s->n_components; c++) {
+    for (int c = 0; c < s->n_components && !s->borrowed; c++) {
         if (s->codes) free(s->codes[c]);
         if (s->counts) free(s->counts[c]);
     }
@@ -354,6 +354,13 @@ extern "C" int mk_fastq_co_host(mk_ctx *ctx, const void *h_text, size_t nbytes, 
     ctx->h_src = nullptr;
     ctx->h_src_all = nullptr;
     return rc;
+}
+
+extern "C" int mk_ctx_set_borrowed_output(mk_ctx *ctx, int on)
+{
+    if (!ctx) return MK_ERR_ARG;
+    ctx->borrow_output = on != 0;
+    return MK_OK;
 }
 
 extern "C" int mk_ctx_set_dedup(mk_ctx *ctx, int on)

@@ -82,6 +82,7 @@ struct mk_ctx {
     int verify_quality = INT_MIN;   // fastq2co(): a base counts iff (signed char)quality byte >= Q (INT_MIN: no check)
     u32 line_limit = 4095;          // fgets(buf, LEN): a line of LEN - 1 bytes or more is split by the reference
     u32 emit_lo = 0, emit_hi = 0xFFFFFFFFu;   // codes are written iff emit_lo <= occurrences <= emit_hi
+    bool borrow_output = false;     // sketches returned as views into the pinned staging block (mk_ctx_set_borrowed_output)
     bool fasta_dedup = false;       // `dist -u`: uniq_fasta2co(), codes occurring once per genome
     void *d_trace = nullptr;        // development aid: phase timestamps of CTA 0 (mk_debug_set_trace)
     Scratch sb[SB_NUM];

@@ -431,6 +431,12 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
             }
             s->n[c] = m;
             s->n_total += m;
+            if (ctx->borrow_output) {      // views into the pinned staging block, valid until the next call on this context
+                s->borrowed = 1;
+                s->codes[c] = h_code + lo;
+                if (with_counts) s->counts[c] = h_cnt + lo;
+                continue;
+            }
             s->codes[c] = (uint32_t *)malloc((size_t)(m ? m : 1) * 4);
             if (!s->codes[c]) return MK_ERR_NOMEM;
             memcpy(s->codes[c], h_code + lo, (size_t)m * 4);

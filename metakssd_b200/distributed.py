@@ -73,6 +73,30 @@ def merge_runs_reference(code: torch.Tensor, pos: torch.Tensor, cnt: torch.Tenso
     return uniq, pmin, torch.clamp(ksum, max=65535).to(cnt.dtype)
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned host buffers allocated
+    afterwards are local to the GPU's PCIe root.  Returns the node (or None when the topology is not exposed)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        bdf = "%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def init_library_comm(sk, group=None):
     """Join the library's own NCCL communicator (csrc/mk_comm.cu): rank 0 draws the unique id, torch.distributed
     (any backend) only carries its 128 bytes to the other ranks."""

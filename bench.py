@@ -300,11 +300,11 @@ def run_ours(args):
         sk.load_markerdb(mdb.comp)
     names_c = M.SpeciesNames(mdb.names)
     max_runs = 0
-    if use_lib_comm:       # block capacity of the exchange: the runs of the fullest shard, with headroom
-        n_local = int(sk.fastq_partial_device(d_text, nbytes, pos_base, 4 * r0, rank == world - 1).n)
-        t = torch.tensor([n_local], dtype=torch.int64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        max_runs = int(t.item()) * 5 // 4 + 4096
+    if use_lib_comm:
+        # block capacity of the exchange (runs one rank sends to one owner / one owner holds after the merge): one
+        # untimed sizing pass of the step, the largest block any rank saw + 1/8 (a pipeline keeps the value for its
+        # next batches).  A block that does not fit fails the step on every rank (MK_ERR_NOMEM), nothing is truncated.
+        max_runs = D.size_exchange_blocks(sk, d_text, nbytes, pos_base, 4 * r0, rank == world - 1)
 
     def sharded_step(text, nb, pb, lb, last, host_text=False):
         """(sketch, tsv) on rank 0, (None, None) elsewhere"""
@@ -425,6 +425,30 @@ def run_ours(args):
             # the kernel), then the sharded path
             return sharded_step(h_text, e_nbytes, pos_base, 4 * r0, rank == world - 1, host_text=True)[1]
 
+        # what the host side can deliver: every rank copies its pinned shard to its GPU at the same time, nothing else
+        # running (the end-to-end step cannot be faster than this copy; at N > 1 the GPUs share PCIe switches / host DRAM)
+        d_probe = torch.empty(e_nbytes, dtype=torch.uint8, device=dev)
+
+        def copy_only():
+            d_probe.copy_(h_text, non_blocking=True)
+
+        cur = torch.cuda.current_stream(dev)
+        copy_only()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(cur)
+        copy_only(); copy_only()
+        c1.record(cur)
+        torch.cuda.synchronize(dev)
+        ms_copy = c0.elapsed_time(c1) / 2
+        if world > 1:
+            t = torch.tensor([ms_copy], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_copy = float(t.item())
+        del d_probe
+
         e_steps = max(2, min(args.steps, 3))
         timed(step_host, 0, 1)
         sk.profile(reset=True)
@@ -434,7 +458,11 @@ def run_ours(args):
         e2e = {"value": world * e2e_reads * READ_LEN / 1e9 / (ms_e / 1e3), "unit": "Gbp/s",
                "h2d_bytes_per_step": int(pe.h2d_bytes // e_steps), "d2h_bytes_per_step": int(pe.d2h_bytes // e_steps),
                "bytes_source": "counted by the library per copy (mk_profile), this rank",
-               "ms_per_step": ms_e, "reads_per_gpu": e2e_reads, "numa_node_of_rank0": numa}
+               "ms_per_step": ms_e, "reads_per_gpu": e2e_reads, "numa_node_of_rank0": numa,
+               "h2d_copy_only": {"ms": ms_copy, "GBps_per_gpu": e_nbytes / 1e6 / ms_copy,
+                                 "GBps_all_gpus": world * e_nbytes / 1e6 / ms_copy,
+                                 "what": "all ranks copy their pinned shard to their GPU at once, max over ranks; "
+                                         "the floor of ms_per_step on this host"}}
         del h_text
 
     if rank != 0:

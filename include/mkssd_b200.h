@@ -255,9 +255,15 @@ int mk_markerdb_load_sharded(mk_ctx *ctx, int component, const uint32_t *ref_cod
                              int n_species);
 /* The whole sharded step for this rank's shard of the FASTQ text (collective: every rank calls it).  Runs go to
  * the owner of their code range in one grouped ncclSend/ncclRecv step (blocks of `max_runs` slots per pair, count
- * in a header; MK_ERR_NOMEM if a block overflows), owners merge, probe their MarkerDB slice (if one is loaded)
- * and send hits and merged runs to rank 0.  On rank 0: `out` = the sketch of the whole file in reference order,
- * `stats` (may be NULL) = per-species statistics; other ranks pass NULL / get nothing. */
+ * in a header), owners merge, probe their MarkerDB slice (if one is loaded) and send hits and merged runs to
+ * rank 0.  A block that does not fit — one sent, or an owner's merged range — fails the step with MK_ERR_NOMEM on
+ * EVERY rank (the flag is reduced inside the step; nothing is truncated).  The code ranges are quantiles of the
+ * law the codes of unbiased sequence follow, so a block holds about 1/world of a shard's runs.
+ * mk_comm_last_block_need(): the largest block this rank saw in the last step (also after MK_ERR_NOMEM): the
+ * maximum over the ranks, plus headroom, is the `max_runs` of the next batch.
+ * On rank 0: `out` = the sketch of the whole file in reference order, `stats` (may be NULL) = per-species
+ * statistics; other ranks pass NULL / get nothing. */
+int mk_comm_last_block_need(mk_ctx *ctx, uint64_t *need);
 int mk_fastq_koc_sharded_device(mk_ctx *ctx, const void *d_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,
                                 int is_last, uint64_t max_runs, mk_sketch *out, mk_species_stat *stats);
 int mk_fastq_koc_sharded_host(mk_ctx *ctx, const void *h_text, size_t nbytes, uint64_t pos_base, uint64_t line_base,

@@ -93,7 +93,7 @@ EXPORTS = [
     "mk_runs_finalize_device", "mk_runs_finalize_distinct_device", "mk_runs_merge_device", "mk_count_newlines_device", "mk_synth_fastq_device",
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
-    "mk_comm_unique_id", "mk_comm_init", "mk_comm_destroy", "mk_markerdb_load_sharded", "mk_fastq_koc_sharded_device",
+    "mk_comm_unique_id", "mk_comm_init", "mk_comm_destroy", "mk_comm_last_block_need", "mk_markerdb_load_sharded", "mk_fastq_koc_sharded_device",
     "mk_fastq_koc_sharded_host", "mk_set_group", "mk_set_uniq_union", "mk_set_operate", "mk_free",
 ]
 
@@ -175,6 +175,7 @@ def load():
     L.mk_comm_unique_id.argtypes = [vp, sz]
     L.mk_comm_init.argtypes = [vp, vp, i32, i32]
     L.mk_comm_destroy.argtypes = [vp]
+    L.mk_comm_last_block_need.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mk_markerdb_load_sharded.argtypes = [vp, i32, vp, vp, i32]
     L.mk_fastq_koc_sharded_device.argtypes = [vp, vp, sz, u64, u64, i32, u64, C.POINTER(MkSketch), vp]
     L.mk_fastq_koc_sharded_host.argtypes = [vp, vp, sz, u64, u64, i32, u64, C.POINTER(MkSketch), vp]
@@ -295,6 +296,7 @@ class Sketcher:
             self._h = C.c_void_p()
             raise MkError(rc, self._L.mk_strerror(rc).decode())
         self.info = MkInfo()
+        self.device = device
         self._L.mk_ctx_info(self._h, C.byref(self.info))
 
     def close(self):
@@ -536,6 +538,12 @@ class Sketcher:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         self._ck(self._L.mk_comm_init(self._h, C.c_char_p(unique_id), rank, world))
         self.rank, self.world = rank, world
+
+    def comm_last_block_need(self) -> int:
+        """Largest exchange block this rank saw in the last sharded step (valid after MK_ERR_NOMEM too)."""
+        v = C.c_uint64()
+        self._ck(self._L.mk_comm_last_block_need(self._h, C.byref(v)))
+        return int(v.value)
 
     def load_markerdb_sharded(self, ref_comp):
         """Every rank passes the WHOLE MarkerDB; the library keeps this rank's code-range slice resident."""

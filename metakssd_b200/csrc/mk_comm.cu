@@ -33,6 +33,7 @@ struct NcclApi {
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -55,7 +56,7 @@ bool load_nccl(char *err, size_t errlen)
     if (!g_nccl.field) { snprintf(err, errlen, "NCCL symbol %s is missing", name); return false; }
     SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommDestroy, "ncclCommDestroy")
     SYM(GroupStart, "ncclGroupStart") SYM(GroupEnd, "ncclGroupEnd") SYM(Send, "ncclSend") SYM(Recv, "ncclRecv")
-    SYM(GetErrorString, "ncclGetErrorString")
+    SYM(GetErrorString, "ncclGetErrorString") SYM(AllReduce, "ncclAllReduce")
 #undef SYM
     g_nccl.ok = true;
     return true;
@@ -113,11 +114,32 @@ extern "C" int mk_comm_destroy(mk_ctx *ctx)
     return MK_OK;
 }
 
-// first code of rank p's range: the code space cut into `world` equal parts
+// First code of rank p's range.  A code leads with the high bases of the canonical k-mer (the smaller of a k-mer and
+// its reverse complement), so over the code space [0, 1) the codes of unbiased sequence follow the density 2 (1 - x)
+// of the minimum of two uniform values; the ranges are the quantiles of that law,
+//     edge_p = 2^code_bits * (1 - sqrt(1 - p / world)),
+// which gives every owner the same share of the runs and of the MarkerDB (equal-width ranges gave the first of two
+// owners two thirds).  Integer arithmetic only, so every rank and the MarkerDB loader agree on the cut.
+static u64 isqrt_u128(unsigned __int128 x)
+{
+    if (x == 0) return 0;
+    u64 r = (u64)sqrtl((long double)x);
+    while ((unsigned __int128)r * r > x) r--;
+    while ((unsigned __int128)(r + 1) * (r + 1) <= x) r++;
+    return r;
+}
+
 static inline u64 range_edge(int p, int world, int code_bits)
 {
-    return (u64)(((unsigned __int128)p << code_bits) / (unsigned)world);
+    if (p <= 0) return 0;
+    if (p >= world) return ~0ull;
+    const unsigned __int128 x = (((unsigned __int128)(unsigned)(world - p)) << (2 * code_bits)) / (unsigned)world;
+    u64 r = isqrt_u128(x);
+    if ((unsigned __int128)r * r < x) r++;                 // ceiling
+    return ((u64)1 << code_bits) - r;
 }
+
+struct RangeEdges { u64 e[65]; };
 
 // ---- MarkerDB slice of this rank -------------------------------------------------------------------
 extern "C" int mk_markerdb_load_sharded(mk_ctx *ctx, int component, const uint32_t *ref_codes, const uint64_t *ref_index,
@@ -136,7 +158,7 @@ extern "C" int mk_markerdb_load_sharded(mk_ctx *ctx, int component, const uint32
     for (int s = 0; s < n_species; s++) {
         for (u64 i = ref_index[s]; i < ref_index[s + 1]; i++) {
             const u64 full = ((u64)ref_codes[i] << ccb) | (u64)component;      // code % component_num == component
-            int p = (int)(((unsigned __int128)full * (unsigned)W) >> cb);        // owner of the code (then corrected)
+            int p = (int)(((unsigned __int128)full * (unsigned)W) >> cb);        // a first guess of the owner, then corrected
             if (p >= W) p = W - 1;
             while (p > 0 && full < edges[(size_t)p]) p--;
             while (p + 1 < W && full >= edges[(size_t)p + 1]) p++;
@@ -150,12 +172,12 @@ extern "C" int mk_markerdb_load_sharded(mk_ctx *ctx, int component, const uint32
 
 // ---- exchange ------------------------------------------------------------------------------------------
 // cut[p] = first run whose code belongs to rank p (runs are sorted by code); cut[world] = n
-__global__ void k_range_cuts(const u64 *__restrict__ code, u64 n, int world, int code_bits, u64 *__restrict__ cut)
+__global__ void k_range_cuts(const u64 *__restrict__ code, u64 n, int world, RangeEdges E, u64 *__restrict__ cut)
 {
     int p = threadIdx.x;
     if (p > world) return;
     if (p == world) { cut[p] = n; return; }
-    const u64 edge = (u64)(((unsigned __int128)p << code_bits) / (unsigned)world);
+    const u64 edge = E.e[p];
     u64 a = 0, b = n;
     while (a < b) { u64 m = (a + b) >> 1; if (code[m] < edge) a = m + 1; else b = m; }
     cut[p] = a;
@@ -172,7 +194,7 @@ k_pack_blocks(const u64 *__restrict__ code, const u64 *__restrict__ pos, const u
     const int p = (int)(i / cap);
     const u64 j = i - (u64)p * cap;
     const u64 lo = cut[p], m = cut[p + 1] - lo;
-    if (j == 0) { hdr[2 * p] = m < cap ? m : cap; hdr[2 * p + 1] = m > cap ? 1ull : 0ull; }
+    if (j == 0) { hdr[2 * p] = m < cap ? m : cap; hdr[2 * p + 1] = m > cap ? m : 0ull; }      // (overflow: the size it needed)
     if (j < m) { o_code[i] = code[lo + j]; o_pos[i] = pos[lo + j]; o_cnt[i] = cnt[lo + j]; }
     else { o_code[i] = EMPTY64; o_pos[i] = 0; o_cnt[i] = 0; }
 }
@@ -251,6 +273,7 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
     const int W = ctx->world, me = ctx->rank;
     const u64 cap = max_runs;
     if (out) memset(out, 0, sizeof(*out));
+    MkPhaseClock pc(ctx->stream);
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
     // ---- 1. runs to their owners --------------------------------------------------------------------
     u64 *cut, *s_hdr, *s_code, *s_pos, *r_hdr, *r_code, *r_pos;
@@ -264,14 +287,18 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
     CKR(mk_scratch(ctx, SB_X_RCODE, (size_t)W * cap, &r_code));
     CKR(mk_scratch(ctx, SB_X_RPOS, (size_t)W * cap, &r_pos));
     CKR(mk_scratch(ctx, SB_X_RCNT, (size_t)W * cap, &r_cnt));
-    k_range_cuts<<<1, W + 1, 0, ctx->stream>>>((const u64 *)runs.d_code, runs.n, W, ctx->info.code_bits, cut);
+    RangeEdges E;
+    for (int p = 0; p <= W; p++) E.e[p] = range_edge(p, W, ctx->info.code_bits);
+    k_range_cuts<<<1, W + 1, 0, ctx->stream>>>((const u64 *)runs.d_code, runs.n, W, E, cut);
     LAUNCH_COUNT(ctx);
     const u64 tot = (u64)W * cap;
     k_pack_blocks<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>((const u64 *)runs.d_code, (const u64 *)runs.d_firstpos,
                                                                         runs.d_count, cut, W, cap, s_hdr, s_code, s_pos, s_cnt);
     LAUNCH_COUNT(ctx);
     CK(cudaGetLastError());
+    pc.mark("x: cuts + pack");
     CKR(exchange_blocks(ctx, false, cap, s_hdr, s_code, s_pos, s_cnt, r_hdr, r_code, r_pos, r_cnt));
+    pc.mark("x: runs exchange");
     // ---- 2. merge on the owner (empty slots are skipped) -------------------------------------------------
     mk_runs merged;
     CKR(mk_runs_merge_device(ctx, (const uint64_t *)r_code, (const uint64_t *)r_pos, r_cnt, tot, &merged));
@@ -280,7 +307,13 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->prof.d2h_bytes += sizeof(u64) * 2 * (u64)W;
     bool overflow = merged.n > cap;
-    for (int p = 0; p < W; p++) overflow = overflow || h_hdr[2 * p + 1] != 0;
+    ctx->last_block_need = merged.n;
+    for (int p = 0; p < W; p++) {
+        overflow = overflow || h_hdr[2 * p + 1] != 0;
+        const u64 need = h_hdr[2 * p + 1] ? h_hdr[2 * p + 1] : h_hdr[2 * p];
+        if (need > ctx->last_block_need) ctx->last_block_need = need;
+    }
+    pc.mark("x: owner merge");
     // ---- 3. rank-local composite against this rank's MarkerDB slice ---------------------------------------
     const bool with_composite = !ctx->mdb.empty() && !ctx->mdb_shard_sizes.empty();
     u64 *hit_blk = nullptr;
@@ -325,6 +358,7 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
             LAUNCH_COUNT(ctx);
         }
     }
+    pc.mark("x: slice composite");
     // ---- 4. merged runs and hits to rank 0 -----------------------------------------------------------------
     {
         // block 0 of the send arrays <- this rank's merged runs (padded)
@@ -336,6 +370,10 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
                                                                             merged.d_count, one_cut, 1, cap, s_hdr, s_code, s_pos, s_cnt);
         LAUNCH_COUNT(ctx);
         CKR(exchange_blocks(ctx, true, cap, s_hdr, s_code, s_pos, s_cnt, r_hdr, r_code, r_pos, r_cnt));
+        // a block that did not fit anywhere fails the step on EVERY rank (one more reduction of a single word)
+        ctx->h_xflag = overflow ? 1 : 0;
+        CK(cudaMemcpyAsync(one_cut + 4, &ctx->h_xflag, 8, cudaMemcpyHostToDevice, ctx->stream));
+        NK(g_nccl.AllReduce(one_cut + 4, one_cut + 4, 1, ncclUint64, ncclMax, (ncclComm_t)ctx->comm, ctx->stream));
         if (with_composite) {
             ncclComm_t comm = (ncclComm_t)ctx->comm;
             NK(g_nccl.GroupStart());
@@ -355,12 +393,18 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
             NK(g_nccl.GroupEnd());
         }
     }
+    {
+        u64 *flag;
+        CKR(mk_scratch(ctx, SB_X_CUT, (size_t)W + 8, &flag));
+        CK(cudaMemcpyAsync(&ctx->h_xflag, flag + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     cudaEventRecord(ctx->ev3, ctx->stream);
+    pc.mark("x: gather to rank 0");
     if (me != 0) {
         CK(cudaStreamSynchronize(ctx->stream));
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.exchange_ms += ms;
-        if (overflow) {
+        if (overflow || ctx->h_xflag) {
             snprintf(ctx->err, sizeof(ctx->err), "sharded step: more than max_runs = %llu runs for one code range", (unsigned long long)cap);
             return MK_ERR_NOMEM;
         }
@@ -374,7 +418,7 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
         if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.exchange_ms += ms;
     }
     for (int p = 0; p < W; p++) overflow = overflow || h_hdr[2 * p + 1] != 0;
-    if (overflow) {
+    if (overflow || ctx->h_xflag) {
         snprintf(ctx->err, sizeof(ctx->err), "sharded step: more than max_runs = %llu runs for one code range", (unsigned long long)cap);
         return MK_ERR_NOMEM;
     }
@@ -403,7 +447,19 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
         }
         if (stats) CKR(mk_composite_stats(ctx, stats));
     }
-    if (out) return mk_runs_finalize_device(ctx, (const uint64_t *)r_code, (const uint64_t *)r_pos, r_cnt, tot, out);
+    pc.mark("x: hits -> statistics");
+    if (out) {       // the gathered blocks hold disjoint ascending code ranges, every code once
+        u64 h_n[64];
+        for (int p = 0; p < W; p++) h_n[p] = h_hdr[2 * p];
+        return mk_runs_finalize_blocks(ctx, r_code, r_pos, r_cnt, W, cap, h_n, out);
+    }
+    return MK_OK;
+}
+
+extern "C" int mk_comm_last_block_need(mk_ctx *ctx, uint64_t *need)
+{
+    if (!ctx || !need) return MK_ERR_ARG;
+    *need = ctx->last_block_need;
     return MK_OK;
 }
 

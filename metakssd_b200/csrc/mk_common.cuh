@@ -106,6 +106,8 @@ struct mk_ctx {
     const uint8_t *h_src_all = nullptr;   // same pointer; plain upload if the pipelined path is not taken
     std::vector<cudaEvent_t> chunk_ev;
     u64 h_maxpos = 0;                     // read-back slot of mk_runs_finalize_device
+    u64 last_block_need = 0;              // largest block the last sharded step saw on this rank (sent to it, or merged by it)
+    u64 h_xflag = 0;                      // read-back slot of the sharded step's collective overflow flag
     u64 last_newlines = 0;                // line_base + newlines of the shard mk_fastq_partial_device saw last
     // device copy of the last single-file -A sketch (codes / counts in on-disk order, component bounds)
     const u32 *last_out_code = nullptr;
@@ -126,7 +128,8 @@ struct MkPhaseClock {
         if (!on) return;
         cudaStreamSynchronize(st);
         auto n = std::chrono::steady_clock::now();
-        fprintf(stderr, "[mk timing] %-22s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        const char *rk = getenv("RANK");
+        fprintf(stderr, "[mk timing%s%s] %-22s %8.3f ms\n", rk ? " r" : "", rk ? rk : "", what, std::chrono::duration<double, std::milli>(n - t).count());
         t = n;
     }
 };
@@ -220,6 +223,8 @@ int mk_order_and_emit(mk_ctx *ctx, u64 *d_it_key, u32 *d_it_cnt, u64 *d_it_pos, 
                       bool with_counts, bool drop_zero_code, mk_sketch *out);
 int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_base, u64 line_base, bool raw_mode,
                     u64 **d_cand_code, u64 **d_cand_pos, u64 *n_cand, u64 *n_newlines);
+int mk_runs_finalize_blocks(mk_ctx *ctx, const u64 *d_code, const u64 *d_firstpos, const u32 *d_count, int W, u64 cap,
+                            const u64 *h_counts, mk_sketch *out);
 int mk_composite_reserve(mk_ctx *ctx, u64 extra);
 int mk_composite_component_dev(mk_ctx *ctx, int component, const u32 *d_qry, const uint16_t *d_qcnt, u64 q);
 int mk_tail_cut(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, long long *keep_below);

@@ -521,13 +521,16 @@ extern "C" int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t n
     if (!ctx || !runs) return MK_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     u64 *cc = nullptr, *cp = nullptr, n_cand = 0, nl = 0;
+    MkPhaseClock pc(ctx->stream);
     CKR(mk_stream_fastq(ctx, (const uint8_t *)d_text, nbytes, pos_base, line_base, false, &cc, &cp, &n_cand, &nl));
+    pc.mark("p: stream+verify");
     ctx->last_newlines = nl;
     long long keep_below = LLONG_MAX;
     if (is_last && nbytes) {
         CKR(mk_tail_cut(ctx, (const uint8_t *)d_text, nbytes, &keep_below));
         if (keep_below >= 0) keep_below += (long long)pos_base; else keep_below = (long long)pos_base;
     }
+    pc.mark("p: tail cut");
     u64 *it_key, *it_pos, n_items;
     u32 *it_cnt;
     CK(cudaEventRecord(ctx->ev2, ctx->stream));
@@ -536,6 +539,7 @@ extern "C" int mk_fastq_partial_device(mk_ctx *ctx, const void *d_text, size_t n
     int rc = runs_sorted_by_code(ctx, it_key, it_cnt, it_pos, n_items, runs);
     cudaEventRecord(ctx->ev3, ctx->stream);
     cudaEventSynchronize(ctx->ev3);
+    pc.mark("p: reduce -> runs");
     float ms = 0;
     if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.reduce_ms += ms;
     return rc;
@@ -641,6 +645,74 @@ static int runs_finalize(mk_ctx *ctx, const uint64_t *d_code, const uint64_t *d_
         ctx->pos_bits = b;
     }
     int rc = mk_order_and_emit(ctx, it_key, it_cnt, it_pos, n_items, 1, true, false, out);
+    ctx->pos_bits = 64;
+    cudaEventRecord(ctx->ev3, ctx->stream);
+    cudaEventSynchronize(ctx->ev3);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev2, ctx->ev3) == cudaSuccess) ctx->prof.reduce_ms += ms;
+    return rc;
+}
+
+// Blocks gathered from the owners of the code ranges (csrc/mk_comm.cu): block p holds h_counts[p] runs at p * cap, codes
+// ascending inside a block and across blocks and every code once, so the runs are only packed next to each other
+// (no second accumulate) before the slot order is reconstructed.
+struct BlockOffsets { u64 off[65]; };
+
+__global__ void __launch_bounds__(256)
+k_gather_blocks(BlockOffsets B, int W, u64 cap, const u64 *__restrict__ code, const u64 *__restrict__ pos,
+                const u32 *__restrict__ cnt, u64 *__restrict__ it_key, u32 *__restrict__ it_cnt, u64 *__restrict__ it_pos,
+                u64 *__restrict__ maxpos)
+{
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 m = 0;
+    if (i < (u64)W * cap) {
+        const u64 p = i / cap, j = i - p * cap;
+        if (j < B.off[p + 1] - B.off[p]) {
+            const u64 o = B.off[p] + j;
+            it_key[o] = code[i];
+            it_cnt[o] = cnt[i];
+            m = pos[i];
+            it_pos[o] = m;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        u64 x = __shfl_xor_sync(0xffffffffu, m, o);
+        m = x > m ? x : m;
+    }
+    if ((threadIdx.x & 31) == 0 && m) atomicMax((unsigned long long *)maxpos, (unsigned long long)m);
+}
+
+int mk_runs_finalize_blocks(mk_ctx *ctx, const u64 *d_code, const u64 *d_firstpos, const u32 *d_count, int W, u64 cap,
+                            const u64 *h_counts, mk_sketch *out)
+{
+    if (!ctx || !out || W < 1 || W > 64) return MK_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    memset(out, 0, sizeof(*out));
+    BlockOffsets B;
+    B.off[0] = 0;
+    for (int p = 0; p < W; p++) B.off[p + 1] = B.off[p] + (h_counts[p] < cap ? h_counts[p] : cap);
+    const u64 n = B.off[W];
+    u64 *it_key, *it_pos, *d_max;
+    u32 *it_cnt;
+    CK(cudaEventRecord(ctx->ev2, ctx->stream));
+    CKR(mk_scratch(ctx, SB_IT_CODE, (size_t)n + 1, &it_key));
+    CKR(mk_scratch(ctx, SB_IT_CNT, (size_t)n + 1, &it_cnt));
+    CKR(mk_scratch(ctx, SB_IT_POS, (size_t)n + 1, &it_pos));
+    if (n) {
+        CKR(mk_scratch(ctx, SB_MISC, 64, &d_max));
+        CK(cudaMemsetAsync(d_max + 4, 0, 8, ctx->stream));
+        const u64 tot = (u64)W * cap;
+        k_gather_blocks<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(B, W, cap, d_code, d_firstpos, d_count, it_key,
+                                                                              it_cnt, it_pos, d_max + 4);
+        LAUNCH_COUNT(ctx);
+        CK(cudaMemcpyAsync(&ctx->h_maxpos, d_max + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int b = 1;
+        while (b < 64 && (ctx->h_maxpos >> b)) b++;
+        ctx->pos_bits = b;
+    }
+    int rc = mk_order_and_emit(ctx, it_key, it_cnt, it_pos, n, 1, true, false, out);
     ctx->pos_bits = 64;
     cudaEventRecord(ctx->ev3, ctx->stream);
     cudaEventSynchronize(ctx->ev3);

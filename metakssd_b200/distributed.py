@@ -32,7 +32,19 @@ def device_tensor(ptr: int, n: int, dtype: torch.dtype, device) -> torch.Tensor:
 
 
 def code_range_edges(world: int, code_bits: int) -> torch.Tensor:
-    return torch.tensor([(i << code_bits) // world for i in range(world + 1)], dtype=torch.int64)
+    """First code of every rank's range (and 2^code_bits): quantiles of the density 2 (1 - x) the codes of unbiased
+    sequence follow (a code leads with the high bases of the smaller of a k-mer and its reverse complement) —
+    the same integer formula as range_edge() in csrc/mk_comm.cu."""
+    import math
+    edges = [0]
+    for p in range(1, world):
+        x = ((world - p) << (2 * code_bits)) // world
+        r = math.isqrt(x)
+        if r * r < x:
+            r += 1
+        edges.append((1 << code_bits) - r)
+    edges.append(1 << code_bits)
+    return torch.tensor(edges, dtype=torch.int64)
 
 
 def split_sizes_by_code_range(codes: torch.Tensor, world: int, code_bits: int) -> list:
@@ -152,3 +164,33 @@ def sketch_sharded(sk, d_text, nbytes: int, pos_base: int, line_base: int, is_la
     out = sk.runs_finalize_device(gc, gp, gk, int(gc.numel()), distinct=True)   # owners' ranges are disjoint
     _mark("finalize")
     return out
+
+
+def size_exchange_blocks(sk, text, nbytes: int, pos_base: int, line_base: int, is_last: bool, host_text: bool = False,
+                         group=None) -> int:
+    """Collective.  Block capacity (`max_runs`) for Sketcher.fastq_koc_sharded() on batches like this one: one sizing
+    pass of the step; a capacity that turns out too small fails on every rank together (MK_ERR_NOMEM), the ranks
+    agree on the size that was needed and repeat.  Returns the largest block any rank saw plus 1/8 headroom — a
+    pipeline keeps using the value for its next batches and comes back here when a step reports MK_ERR_NOMEM."""
+    from .api import MkError
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", sk.device)
+    part = sk.fastq_partial_host(text, nbytes, pos_base, line_base, is_last) if host_text else \
+        sk.fastq_partial_device(text, nbytes, pos_base, line_base, is_last)
+    t = torch.tensor([int(part.n)], dtype=torch.int64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    cap = int(t.item()) * 3 // (2 * world) + 4096            # 1.5 x the even share of the fullest shard
+    for _ in range(4):
+        try:
+            sk.fastq_koc_sharded(text, nbytes, pos_base, line_base, is_last, cap, host_text=host_text, want_stats=False)
+            failed = False
+        except MkError as e:
+            if e.code != -4:                                 # MK_ERR_NOMEM
+                raise
+            failed = True
+        t = torch.tensor([sk.comm_last_block_need()], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        cap = int(t.item()) * 9 // 8 + 1024
+        if not failed:
+            return cap
+    raise RuntimeError("exchange block capacity did not settle")

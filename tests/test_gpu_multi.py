@@ -45,9 +45,9 @@ WORKER = textwrap.dedent('''
     mdb = W.build_markerdb(sk, spec)
     D.init_library_comm(sk)
     sk.load_markerdb_sharded(mdb.comp)
+    cap = D.size_exchange_blocks(sk, d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1)
     n_local = int(sk.fastq_partial_device(d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1).n)
-    t = torch.tensor([n_local], dtype=torch.int64, device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    cap = int(t.item()) * 5 // 4 + 4096
+    assert (cap - 1024) * 8 / 9 < 0.8 * n_local, (cap, n_local)     # balanced code ranges: a block is a fraction of a shard's runs
     got_l, stats_l = sk.fastq_koc_sharded(d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, cap)
     got_lh, stats_lh = sk.fastq_koc_sharded(h, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, cap, host_text=True)
     # a block capacity that is too small must be reported, not silently truncated
@@ -56,8 +56,8 @@ WORKER = textwrap.dedent('''
         sk.fastq_koc_sharded(d, nb, spec.fastq_bytes(0, r0), 0, rank == world - 1, 64)
     except M.MkError as e:
         failed = 1 if e.code == -4 else 0
-    f = torch.tensor([failed], dtype=torch.int64, device=dev); dist.all_reduce(f, op=dist.ReduceOp.MAX)
-    assert int(f.item()) == 1, "an overflowing exchange block went unnoticed"
+    f = torch.tensor([failed], dtype=torch.int64, device=dev); dist.all_reduce(f, op=dist.ReduceOp.MIN)
+    assert int(f.item()) == 1, "an overflowing exchange block must fail the step on every rank"
     if rank == 0:
         nball = spec.fastq_bytes(0, world * per)
         full = torch.empty(nball + 256, dtype=torch.uint8, device=dev)

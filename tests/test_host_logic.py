@@ -135,3 +135,22 @@ def test_c_coverage_formatter_matches_python(lib_built):
     assert got == want and want.count("\n") > 100
     assert coverage_tsv("q", SpeciesNames(names), np.zeros(S, dtype=STATS_DTYPE)) == ""
 
+
+
+def test_code_range_edges_balance_the_owners(oracle):
+    """distributed.code_range_edges / range_edge() in csrc/mk_comm.cu: quantiles of the min-of-two-uniforms law the
+    codes follow, so every owner gets about the same share of a sketch (equal-width ranges gave the first of two
+    owners two thirds)."""
+    from metakssd_b200 import distributed as D
+    p = oracle.params(11, 6, 3)
+    _, perm = oracle.make_shuf(5, 11, 6, 3)
+    S = oracle.synth(7, 20, 200_000, 150)
+    codes = np.asarray(oracle.fastq_koc(p, perm, S.fastq(0, 400_000)).codes, dtype=np.int64)
+    assert codes.size > 1000
+    for world in (2, 4, 8):
+        e = D.code_range_edges(world, 32).numpy()
+        assert e[0] == 0 and e[-1] == 1 << 32 and np.all(np.diff(e) > 0)
+        share = np.histogram(codes, bins=e)[0] / codes.size
+        assert share.max() < 1.35 / world and share.min() > 0.65 / world, (world, share)
+    even = np.histogram(codes, bins=[0, 1 << 31, 1 << 32])[0] / codes.size
+    assert even[0] > 0.6                                   # what equal-width ranges would have done

@@ -24,7 +24,7 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmkssd_b200.so")
+LIB_PATH = os.environ.get("MK_LIB_PATH") or os.path.join(HERE, "libmkssd_b200.so")      # (MK_LIB_PATH: development builds)
 
 MK_OK = 0
 ERRORS = {

@@ -117,7 +117,7 @@ int mk_fastq_koc_device(mk_ctx *ctx, const void *d_text, size_t nbytes, mk_sketc
  * is chunked and overlapped with the kernels. */
 int mk_fastq_koc_host(mk_ctx *ctx, const void *h_text, size_t nbytes, mk_sketch *out);
 /* Same as the reference call (iseq2comem.c:664-673): the text of `<pipecmd or "zcat -fc"> <path>`.  Streamed:
- * line-aligned chunks (MK_INGEST_CHUNK_BYTES, default 64 MB) go through a small ring of pinned buffers, the
+ * line-aligned chunks (MK_INGEST_CHUNK_BYTES, default 16 MB) go through a small ring of pinned buffers, the
  * copy of chunk i+1 and the read of chunk i+2 run under the sketch of chunk i; host memory does not grow
  * with the input.  A plain (uncompressed) file is read directly with parallel pread() instead of a pipe. */
 int mk_fastq_koc_file(mk_ctx *ctx, const char *path, const char *pipecmd, mk_sketch *out);

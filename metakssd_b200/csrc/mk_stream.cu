@@ -121,16 +121,34 @@ __device__ __forceinline__ bool verify_kmer(const uint8_t *t, const KParams &kp,
 }
 
 
-template <int ROTOFF, u32 WORDMASK, int J>
+// Filter word at byte offset `off`.  FIXED = true: the filter is the first object of the kernel's dynamic shared
+// memory and the kernel has no static shared memory, so it starts at CTA-shared address MK_DYN_SMEM_BASE (the
+// 1 KB below it is reserved by the system on sm_100) and the load is ONE `LDS R, [R + 0x400]`; through the generic
+// pointer the compiler adds the (shared::cluster) window base in a separate instruction per lookup.  The
+// kernel checks the assumption once (FLAG_SMEM_BASE).
+#define MK_DYN_SMEM_BASE 1024
+template <bool FIXED>
+__device__ __forceinline__ u32 filter_word(const u32 *bm, u32 off)
+{
+    if constexpr (FIXED) {
+        u32 w;
+        asm("ld.shared.u32 %0, [%1+1024];" : "=r"(w) : "r"(off));
+        return w;
+    } else {
+        return *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + off);
+    }
+}
+
+template <int ROTOFF, u32 WORDMASK, int J, bool FIXED>
 __device__ __forceinline__ void probe_one(const u32 (&A)[4], const u32 *bm, u32 &hits)
 {
     constexpr int NEEDV = ROTOFF;     // bits 0..1 of v are masked off, bits 2..ROTOFF-1 index the word
     u32 v = take_bits<2 * J, NEEDV>(A);
     u32 r = take_bits<2 * J + ROTOFF, 5>(A);
-    u32 word = *reinterpret_cast<const u32 *>(reinterpret_cast<const char *>(bm) + (v & WORDMASK));
+    u32 word = filter_word<FIXED>(bm, v & WORDMASK);
     u32 rot = __funnelshift_l(word, word, r);
     hits = __funnelshift_l(rot, hits, 1);
-    if constexpr (J < 31) probe_one<ROTOFF, WORDMASK, J + 1>(A, bm, hits);
+    if constexpr (J < 31) probe_one<ROTOFF, WORDMASK, J + 1, FIXED>(A, bm, hits);
 }
 
 // Packed bases of one block: A[0..2], position j's inner window starting at bit 2j (+2*spare).
@@ -164,12 +182,12 @@ __device__ __forceinline__ void load_block(const uint8_t *blk, int shift_s, u32 
 // Probe the 32 k-mer end positions of one aligned 32-byte block against the bitmap.
 // blk = shared-memory address of the block's first byte.  Bit j of the result = position j hit.
 // A[0..2] receive the packed bases, position j's inner window starting at bit 2j.
-template <int ROTOFF, u32 WORDMASK, int PREW>
+template <int ROTOFF, u32 WORDMASK, int PREW, bool FIXED = false>
 __device__ __forceinline__ u32 probe_block(const uint8_t *blk, const u32 *bm, int shift_s, u32 (&A)[4])
 {
     load_block<PREW>(blk, shift_s, A);
     u32 hits = 0;
-    probe_one<ROTOFF, WORDMASK, 0>(A, bm, hits);
+    probe_one<ROTOFF, WORDMASK, 0, FIXED>(A, bm, hits);
     return __brev(hits);
 }
 
@@ -591,9 +609,12 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 //   count-ahead (WS_NCW)    a team that counts the newlines of whole groups straight from global
 //                           memory, WS_WINDOW x gridDim groups ahead of the load front, and publishes
 //                           one packed descriptor per group (read by every CTA's resolver)
-//   scan        (2 teams)   newline mask + in-tile prefix of newline counts per 32-byte block
-//                                                                                  -> scanned[s]
-//   mask        (2 teams)   sequence-byte mask per block, item list of the tile   -> ready[s]
+//   front       (2 teams)   every warp of the team scans one 2 KB chunk (newline mask + in-tile prefix of
+//                           newline counts per 32-byte block), the team meets on a named barrier, then
+//                           every warp masks one 64-block unit (sequence-byte mask per block, item list
+//                           of the tile)                                             -> ready[s]
+//                           (-DWS_SPLIT_FRONT: the earlier separate scan and mask teams with a `scanned`
+//                           mbarrier between them; 1 % slower)
 //   probe       (2 groups)  probe a static, per-tile rotated share of the items   -> done[s]
 //
 // Teams / groups take alternating tiles (k % 2).  The k-th tile of a CTA always uses stage k % NS, so
@@ -601,6 +622,9 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 // ================================================================================================
 #ifndef WS_NS
 #define WS_NS 6        // ring stages
+#endif
+#ifndef WS_FIXED_FILTER_BASE
+#define WS_FIXED_FILTER_BASE true   // filter lookups as LDS [R + 0x400] (see filter_word())
 #endif
 #ifndef WS_TILE
 #define WS_TILE 12288  // tile-proper bytes (multiple of 2048)
@@ -630,8 +654,19 @@ __global__ void __launch_bounds__(MK_STREAM_THREADS, 1) k_stream(const __grid_co
 #define WS_G 4          // tiles per ticket (consecutive tiles of one CTA)
 #endif
 #define WS_ROLE0 (2 + WS_NCW)   // first front-end warp (0 = loader, 1 = resolver, then the count warps)
+#ifndef WS_SPLIT_FRONT
+#define WS_FUSED_FRONT 1
+#endif
+#ifdef WS_FUSED_FRONT
+// one front team per probe group does scan AND mask of its tile (a named barrier in between): every warp scans one
+// 2 KB chunk and masks one 64-block unit, so the two stages take half the time each and one mbarrier hand-over
+// is gone
+#define WS_SCT (WS_NFW / WS_NPG)
+#define WS_MKT (WS_NFW / WS_NPG)
+#else
 #define WS_SCT (WS_NSW / WS_NPG)   // warps per scan team
 #define WS_MKT (WS_NMW / WS_NPG)   // warps per mask team
+#endif
 #define WS_THREADS (32 * (WS_ROLE0 + WS_NFW + WS_NPG * WS_NPW))
 static_assert(WS_NSW % WS_NPG == 0 && WS_NMW % WS_NPG == 0, "teams");
 static_assert(WS_G == 4 && WS_TILE < 16384, "descriptor packing");
@@ -724,6 +759,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         S.cticket = 0; S.csum[0] = 0; S.csum[1] = 0; S.abort = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (WS_FIXED_FILTER_BASE && tid == 0 && ((u32)__cvta_generic_to_shared(bm) & 0xFFFFFFu) != MK_DYN_SMEM_BASE)
+        atomicOr(A.flags, FLAG_SMEM_BASE);      // (filter_word<true> would read the wrong words: the host refuses the result)
     __syncthreads();   // the only block-wide barrier of the kernel
 
     const u32 TB = A.tile_bytes;
@@ -989,8 +1026,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
         // WS_NPG tile periods for its share of a tile.
         const u32 fw = wid - WS_ROLE0;
         const bool is_scan = fw < WS_NSW;
+#ifdef WS_FUSED_FRONT
+        const u32 team = fw / WS_SCT, member = fw % WS_SCT;
+#else
         const u32 team = (is_scan ? fw : fw - WS_NSW) / (is_scan ? WS_SCT : WS_MKT);
         const u32 member = (is_scan ? fw : fw - WS_NSW) % (is_scan ? WS_SCT : WS_MKT);
+#endif
         auto scan = [&](u32 s, u32 t, u32 k) {
             WsStage &G = S.st[s];
             uint8_t *tx = tbuf + s * WS_TBUF;
@@ -1046,6 +1087,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             }
             fence_proxy_async();
             __syncwarp();
+#ifdef WS_FUSED_FRONT
+            named_bar_sync(4 + WS_NPG + team, 32u * WS_SCT);     // the whole tile is scanned
+            if (member == 0 && !RAW) {      // a line of 4095+ bytes (fgets splits it, MK_ERR_LONG_LINE) covers a whole chunk
+                const u32 v = lane < NCHUNK ? G.ctot[lane] : 1u;
+                const u32 cend = (lane + 1u) * 2048u < TB ? (lane + 1u) * 2048u : TB;
+                if (__any_sync(0xffffffffu, lane < NCHUNK && v == 0 && cend <= tb) && lane == 0)
+                    atomicOr(A.flags, FLAG_MAYBE_LONG);
+            }
+            return;
+#endif
             // The warp of the team that finishes the tile's scan last turns the per-chunk counts into the
             // in-tile prefix the mask stage needs (the counts other CTAs look back on come from the
             // count-ahead pass, not from here).
@@ -1075,7 +1126,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             WsStage &G = S.st[s];
             const u32 tb = tile_len(t);
             const u32 P = RAW ? 0u : (u32)S.Pn[k];      // k = tile sequence number mod 2 NS
+#ifdef WS_FUSED_FRONT
+            u32 cpre_incl = 0, cpre_v = 0;              // in-tile prefix of the chunks' newline counts, per warp
+            if (!RAW) {
+                cpre_v = lane < NCHUNK ? G.ctot[lane] : 0;
+                cpre_incl = cpre_v;
+#pragma unroll
+                for (int o = 1; o < 16; o <<= 1) {
+                    u32 x = __shfl_up_sync(0xffffffffu, cpre_incl, o);
+                    if (lane >= (u32)o) cpre_incl += x;
+                }
+            }
+#endif
             for (u32 u = member; u < NMUNIT; u += WS_MKT) {
+#ifdef WS_FUSED_FRONT
+                const u32 cpre_u = __shfl_sync(0xffffffffu, cpre_incl - cpre_v, u & 31u);     // (unit u = chunk u)
+#endif
                 u32 pm[2];
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
@@ -1087,7 +1153,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                             pm[h] = lo >= tb ? 0u : (tb - lo >= 32 ? 0xffffffffu : ((1u << (tb - lo)) - 1u));
                         } else {
                             const u32 nl = G.nlm[b];
+#ifdef WS_FUSED_FRONT
+                            const u32 s0 = (P + cpre_u + G.exw[b]) & 3u;
+#else
                             const u32 s0 = (P + G.cpre[b >> 6] + G.exw[b]) & 3u;
+#endif
                             const u32 tgt = (1u - s0) & 3u;
                             // (no "if (nl)": some lane of the warp always has a newline, the branch only costs)
                             const u32 p0 = prefix_xor(nl << 1);
@@ -1110,6 +1180,27 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
             __syncwarp();
             if (lane == 0) { __threadfence_block(); mbar_arrive(&S.ready[s]); }
         };
+#ifdef WS_FUSED_FRONT
+        (void)is_scan;
+        for (u32 k = team, s = team % NS, par = (team / NS) & 1u, k2 = team % (2 * NS);; k += WS_NPG) {
+            if (k != team) {
+                s += WS_NPG; if (s >= NS) { s -= NS; par ^= 1u; }
+                k2 += WS_NPG; if (k2 >= 2 * NS) k2 -= 2 * NS;
+            }
+            if (!role_wait(&S.full[s], nullptr, par, 30, k, 4 + team, WS_SCT, member == 0)) break;
+            const u32 t = S.tile[s];
+            if (t >= A.n_tiles) {                       // end marker: wake this team's probe group, then leave
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.ready[s]);
+                break;
+            }
+            stamp(k, 0);
+            scan(s, t, k2);
+            stamp(k, 1);
+            mask(s, t, k2);
+            stamp(k, 3);
+        }
+#else
         if (is_scan) {
             // (stage, parity and the 2 NS-periodic index follow k incrementally: no divisions in the loops)
             for (u32 k = team, s = team % NS, par = (team / NS) & 1u, k2 = team % (2 * NS);; k += WS_NPG) {
@@ -1144,6 +1235,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 stamp(k, 3);
             }
         }
+#endif
     } else {
         // ======================= probe ==========================================================
         const u32 pg = (wid - WS_ROLE0 - WS_NFW) / WS_NPW, pw = (wid - WS_ROLE0 - WS_NFW) % WS_NPW;
@@ -1167,7 +1259,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_stream_ws(const __grid_consta
                 if (it < n) {
                     const u32 b = G.items[it];
                     u32 Aw[4];
-                    u32 hits = probe_block<ROTOFF, WORDMASK, PREW>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
+                    u32 hits = probe_block<ROTOFF, WORDMASK, PREW, WS_FIXED_FILTER_BASE>(tx + MK_HALO + 32 * b, bm, A.kp.shift_s, Aw);
                     hits &= G.nlm[b];                       // sequence-byte mask by now
                     while (hits) {
                         u32 j = __ffs(hits) - 1;
@@ -1628,6 +1720,11 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
                      (unsigned long long)h[14], (unsigned long long)(h[15] >> 42),
                      (unsigned long long)((h[15] >> 21) & 0x1FFFFF), (unsigned long long)(h[15] & 0x1FFFFF), n_tiles);
             return MK_ERR_CUDA;
+        }
+        if (flags & FLAG_SMEM_BASE) {
+            snprintf(ctx->err, sizeof(ctx->err), "k_stream_ws: dynamic shared memory does not start at CTA-shared address %d "
+                     "(rebuild with -DWS_FIXED_FILTER_BASE=false)", MK_DYN_SMEM_BASE);
+            return MK_ERR_UNSUPPORTED;
         }
         if (v3 && (flags & FLAG_ARENA_FULL)) {       // unusually many short sequence lines: the cursor says what is needed
             arena_items = (size_t)h[7] + 1024;

@@ -32,6 +32,7 @@ struct StreamArgs {
 #define TBUF_STRIDE (MK_HALO + MK_MAX_TILE + 96) // keeps the stage buffers 128-byte aligned
 #define FLAG_LONG_LINE 2u
 #define FLAG_MAYBE_LONG 8u   // some 2 KB chunk holds no newline: the host runs the exact line-length check
+#define FLAG_SMEM_BASE 32u   // the dynamic shared memory of k_stream_ws does not start where filter_word<true> assumes
 #define FLAG_WATCHDOG 4u     // a wait inside k_stream gave up (diagnostics in StreamArgs::wd)
 #define WD_LIMIT (1u << 21)
 

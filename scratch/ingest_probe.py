@@ -24,3 +24,10 @@ for env in ({}, {"MK_INGEST_THREADS": "4"}, {"MK_INGEST_THREADS": "8"}, {"MK_ING
     dt = time.time() - t0
     ph = [l for l in r.stderr.splitlines() if "[host" in l or "sketching" in l or "ctx" in l]
     print(env, "wall %.3f s" % dt, "|", " ; ".join(x.strip() for x in ph)[:400])
+import shutil
+shutil.rmtree(d + "/out2", ignore_errors=True); shutil.copytree(d + "/out", d + "/out2")
+for i in range(2):
+    t0 = time.time()
+    r = subprocess.run(["host/metakssd-b200", "composite", "-r", d + "/out2", "-q", d + "/out"], env=dict(os.environ, MK_TIMING="1"), capture_output=True, text=True)
+    print("composite wall %.3f s" % (time.time() - t0), "|", " ; ".join(x.strip() for x in r.stderr.splitlines() if "timing" in x)[:500])
+t0 = time.time(); subprocess.run(["host/metakssd-b200", "--help"], capture_output=True); print("process start (--help) %.3f s" % (time.time() - t0))

@@ -137,6 +137,27 @@ k_fa_summary(const uint8_t *__restrict__ text, u64 n, const u64 *__restrict__ fi
     u32 wc = 0, kept_all = 0, kept_pre = 0;
     for (u64 s0 = t0; s0 < t0 + FA_TILE && s0 < n; s0 += FA_STEP) {
         const u64 g = s0 + 16ull * lane;
+        // Fast path (nearly every step of a genome): outside a header, the first terminator of the tile already
+        // seen, the whole step inside the text and inside one file, and no '>' in it.  Then nothing but '\n' and
+        // '\r' is dropped and the only possible event is a terminator: three byte compares per word and one
+        // population count, no masks, no carry chain.
+        if (wc == 0 && seen_end && s0 + FA_STEP <= n && !(nb < n_files && file_off[nb] <= s0 + FA_STEP)) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(text + g);
+            const u32 w[4] = {v.x, v.y, v.z, v.w};
+            u32 fn = 0, fd = 0, fg = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const u32 a = eq_bytes(w[i], 0x0A0A0A0Au);
+                fn |= a;
+                fd += __popc(a | eq_bytes(w[i], 0x0D0D0D0Du));
+                fg |= eq_bytes(w[i], 0x3E3E3E3Eu);
+            }
+            if (!__any_sync(0xffffffffu, fg != 0)) {
+                kept_all += 16u - fd;
+                if (__any_sync(0xffffffffu, fn != 0)) kind = 1u;
+                continue;
+            }
+        }
         FaLane L;
         fa_load(text, g, n, L);
         u32 end = L.nl, gt = L.gt;
@@ -260,9 +281,12 @@ k_fa_write(const uint8_t *__restrict__ text, u64 n, const u64 *__restrict__ file
         u32 end = L.nl, gt = L.gt;
         const bool files_here = nb < n_files && file_off[nb] <= s0 + FA_STEP;
         if (files_here) fa_file_ends(file_off, n_files, nb, s0, g, end, gt);
-        u32 wcout;
-        const u32 hdr = fa_header_bits(end, gt, wc, wcout);
-        wc = wcout;
+        u32 hdr = 0;
+        if (wc != 0 || __any_sync(0xffffffffu, gt != 0)) {     // (else: no header in or entering this step, no carry chain)
+            u32 wcout;
+            hdr = fa_header_bits(end, gt, wc, wcout);
+            wc = wcout;
+        }
         const u32 keep = ~hdr & ~L.crnl & L.valid;
         const u32 cnt = __popc(keep);
         u32 incl = cnt;

@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--parity-reads", type=int, default=400_000, help="records of the prefix checked against the oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: equal shards (rank 0 is not given fewer reads for its tail)")
     ap.add_argument("--no-parity", action="store_true")
     a = ap.parse_args()
     c = CONFIGS[a.config]
@@ -396,6 +397,45 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     ms_total, tsv = timed(step_device, 0, args.warmup)      # warm-up outside the profile window
+    balance = None
+    my_reads = per_rank
+    if use_lib_comm and not args.no_balance:
+        # Rank 0 alone turns the gathered runs into the sketch (slot order needs one table) while the other ranks
+        # are already streaming their next shard, and then everybody waits for it at the next exchange.  So rank 0
+        # gets a shard that is shorter by what its tail costs: measured here as the time the other ranks spend in
+        # the first exchange beyond rank 0's own (mk_profile.exchange_wait_ms), over three steady-state steps.
+        # The total number of reads stays world x reads_per_gpu.
+        d_total, history = 0, []
+        for it in range(2):         # the second pass corrects what is left after the first
+            sk.profile(reset=True)
+            timed(step_device, 3, 0)
+            pw = sk.profile()
+            w = torch.tensor([pw.exchange_wait_ms / 3, pw.stream_kernel_ms / 3], dtype=torch.float64, device=dev)
+            allw = [torch.zeros_like(w) for _ in range(world)]
+            dist.all_gather(allw, w)
+            waits = [float(x[0]) for x in allw]
+            stream_ms_per_read = sum(float(x[1]) for x in allw) / (world * per_rank)
+            tail_ms = sum(waits[1:]) / (world - 1) - waits[0]      # > 0: the others wait for rank 0
+            history.append({"exchange_wait_ms_per_rank": waits, "rank0_tail_ms": tail_ms})
+            d_total += int(tail_ms / stream_ms_per_read * (world - 1) / world)
+            d_total = max(0, min(d_total, per_rank * 2 // 5))
+            shares = [per_rank - d_total] + [per_rank + d_total // (world - 1)] * (world - 1)
+            shares[-1] += world * per_rank - sum(shares)
+            starts = [sum(shares[:q]) for q in range(world)]
+            r0, r1 = starts[rank], starts[rank] + shares[rank]
+            my_reads = shares[rank]
+            nbytes = spec.fastq_bytes(r0, r1)
+            pos_base = spec.fastq_bytes(0, r0)
+            d_text = None
+            torch.cuda.empty_cache()
+            d_text = torch.empty(nbytes + 256, dtype=torch.uint8, device=dev)
+            sk.synth_fastq_device(spec.P, spec.cdf32, spec.species, r0, r1, d_text, d_text.numel())
+            max_runs = D.size_exchange_blocks(sk, d_text, nbytes, pos_base, 4 * r0, rank == world - 1)
+            algo_bytes = my_reads * (READ_LEN + 1)
+            timed(step_device, 0, args.warmup)
+        balance = {"reads_per_rank": shares, "passes": history,
+                   "what": "rank 0 (slot order of the gathered sketch, statistics) gets fewer reads so that all ranks reach "
+                           "the next exchange together; total reads unchanged"}
     sk.profile(reset=True)
     ms_total, tsv = timed(step_device, args.steps, 0)
     prof = sk.profile()
@@ -408,10 +448,15 @@ def run_ours(args):
     if not args.no_e2e:
         import psutil
         need = nbytes * world * 1.15
-        e2e_reads = per_rank
+        e2e_reads = my_reads
         if psutil.virtual_memory().available < need + (8 << 30):
-            e2e_reads = max(1_000_000, int(per_rank * (psutil.virtual_memory().available * 0.5) / need))
-            e2e_reads = min(e2e_reads, per_rank)
+            e2e_reads = max(1_000_000, int(my_reads * (psutil.virtual_memory().available * 0.5) / need))
+            e2e_reads = min(e2e_reads, my_reads)
+        e2e_total = e2e_reads
+        if world > 1:
+            t = torch.tensor([e2e_reads], dtype=torch.int64, device=dev)
+            dist.all_reduce(t)
+            e2e_total = int(t.item())
         e_nbytes = spec.fastq_bytes(r0, r0 + e2e_reads)
         numa = D.bind_to_gpu_numa(local)          # the pinned buffer is first touched on the GPU's own NUMA node
         h_text = torch.empty(e_nbytes, dtype=torch.uint8, pin_memory=True)
@@ -427,10 +472,13 @@ def run_ours(args):
 
         # what the host side can deliver: every rank copies its pinned shard to its GPU at the same time, nothing else
         # running (the end-to-end step cannot be faster than this copy; at N > 1 the GPUs share PCIe switches / host DRAM)
-        d_probe = torch.empty(e_nbytes, dtype=torch.uint8, device=dev)
+        probe_bytes = min(e_nbytes, 2 << 30)        # (slices of the pinned text into one 2 GB device buffer)
+        d_probe = torch.empty(probe_bytes, dtype=torch.uint8, device=dev)
 
         def copy_only():
-            d_probe.copy_(h_text, non_blocking=True)
+            for o in range(0, e_nbytes, probe_bytes):
+                m = min(probe_bytes, e_nbytes - o)
+                d_probe[:m].copy_(h_text[o:o + m], non_blocking=True)
 
         cur = torch.cuda.current_stream(dev)
         copy_only()
@@ -448,6 +496,7 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_copy = float(t.item())
         del d_probe
+        torch.cuda.empty_cache()
 
         e_steps = max(2, min(args.steps, 3))
         timed(step_host, 0, 1)
@@ -455,7 +504,7 @@ def run_ours(args):
         ms_e, tsv_e = timed(step_host, e_steps, 0)
         pe = sk.profile()
         ms_e /= e_steps
-        e2e = {"value": world * e2e_reads * READ_LEN / 1e9 / (ms_e / 1e3), "unit": "Gbp/s",
+        e2e = {"value": e2e_total * READ_LEN / 1e9 / (ms_e / 1e3), "unit": "Gbp/s",
                "h2d_bytes_per_step": int(pe.h2d_bytes // e_steps), "d2h_bytes_per_step": int(pe.d2h_bytes // e_steps),
                "bytes_source": "counted by the library per copy (mk_profile), this rank",
                "ms_per_step": ms_e, "reads_per_gpu": e2e_reads, "numa_node_of_rank0": numa,
@@ -487,7 +536,7 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "kernel_ms_per_launch": k_ms, "algorithmic_bytes_per_launch": algo_bytes,
                 "text_bytes_per_launch": nbytes, "kernel_share_of_step": k_ms / ms_step,
-                "kernel_Gbp_s": bases / 1e9 / (k_ms / 1e3)}
+                "kernel_Gbp_s": my_reads * READ_LEN / 1e9 / (k_ms / 1e3)}
 
     cpu = cli = None
     if world == 1 and not args.no_cpu_baseline:
@@ -502,7 +551,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": workload_name(args, world), "config": args.config, "k": K, "subk": SUBK, "L": L,
-                   "reads_per_gpu": per_rank, "read_len": READ_LEN, "species": args.species, "genome_len": args.genome_len,
+                   "reads_per_gpu": per_rank, "shard_balance": balance,
+                   "read_len": READ_LEN, "species": args.species, "genome_len": args.genome_len,
                    "markerdb_codes": mdb.n_codes, "l2_policy": "input (%.1f GB per GPU) is far larger than L2" % (nbytes / 1e9),
                    "parallelism": ("reads sharded per GPU; runs exchanged by code range in one grouped ncclSend/ncclRecv step inside the "
                                    "library, MarkerDB sharded on the same boundaries (rank-local composite), slot order on rank 0"

@@ -92,6 +92,7 @@ typedef struct mk_profile {
     uint64_t kernel_launches;    /* every kernel launched by this context                   */
     uint64_t h2d_bytes, d2h_bytes;
     double exchange_ms;          /* multi-GPU: pack + NCCL exchange + owner merge + rank-local composite + gather */
+    double exchange_wait_ms;     /* multi-GPU: the first grouped send/recv alone, i.e. mostly the wait for the slowest rank */
 } mk_profile;
 
 const char *mk_strerror(int code);

@@ -60,7 +60,7 @@ class MkProfile(C.Structure):
         ("stream_kernel_ms", C.c_double), ("stream_kernel_launches", C.c_uint64),
         ("stream_kernel_bytes", C.c_uint64), ("reduce_ms", C.c_double), ("composite_ms", C.c_double),
         ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
-        ("exchange_ms", C.c_double),
+        ("exchange_ms", C.c_double), ("exchange_wait_ms", C.c_double),
     ]
 
 

@@ -205,6 +205,8 @@ extern "C" void mk_ctx_destroy(mk_ctx *ctx)
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev2) cudaEventDestroy(ctx->ev2);
     if (ctx->ev3) cudaEventDestroy(ctx->ev3);
+    if (ctx->evx[0]) cudaEventDestroy(ctx->evx[0]);
+    if (ctx->evx[1]) cudaEventDestroy(ctx->evx[1]);
     if (ctx->copy_ev[0]) cudaEventDestroy(ctx->copy_ev[0]);
     if (ctx->copy_ev[1]) cudaEventDestroy(ctx->copy_ev[1]);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

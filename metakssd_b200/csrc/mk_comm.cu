@@ -297,7 +297,10 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
     LAUNCH_COUNT(ctx);
     CK(cudaGetLastError());
     pc.mark("x: cuts + pack");
+    if (!ctx->evx[0]) { CK(cudaEventCreate(&ctx->evx[0])); CK(cudaEventCreate(&ctx->evx[1])); }
+    CK(cudaEventRecord(ctx->evx[0], ctx->stream));
     CKR(exchange_blocks(ctx, false, cap, s_hdr, s_code, s_pos, s_cnt, r_hdr, r_code, r_pos, r_cnt));
+    CK(cudaEventRecord(ctx->evx[1], ctx->stream));
     pc.mark("x: runs exchange");
     // ---- 2. merge on the owner (empty slots are skipped) -------------------------------------------------
     mk_runs merged;
@@ -306,6 +309,10 @@ static int sharded_tail(mk_ctx *ctx, const mk_runs &runs, u64 max_runs, mk_sketc
     CK(cudaMemcpyAsync(h_hdr, r_hdr, sizeof(u64) * 2 * (size_t)W, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->prof.d2h_bytes += sizeof(u64) * 2 * (u64)W;
+    {
+        float ms = 0;       // (the stream has been synchronised: both events are complete)
+        if (cudaEventElapsedTime(&ms, ctx->evx[0], ctx->evx[1]) == cudaSuccess) ctx->prof.exchange_wait_ms += ms;
+    }
     bool overflow = merged.n > cap;
     ctx->last_block_need = merged.n;
     for (int p = 0; p < W; p++) {

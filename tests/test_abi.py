@@ -35,7 +35,7 @@ def test_error_strings(lib_built):
 def test_struct_layouts_match_header(lib_built):
     assert C.sizeof(lib_built.MkInfo) == 13 * 4
     assert C.sizeof(lib_built.api.MkSketch) == 48          # (+ `borrowed` since round 2)
-    assert C.sizeof(lib_built.api.MkProfile) == 9 * 8
+    assert C.sizeof(lib_built.api.MkProfile) == 10 * 8
     assert C.sizeof(lib_built.api.MkSpeciesStat) == 24
     assert C.sizeof(lib_built.MksParams) == 40
 

@@ -399,6 +399,15 @@ def run_ours(args):
     ms_total, tsv = timed(step_device, 0, args.warmup)      # warm-up outside the profile window
     balance = None
     my_reads = per_rank
+    eq = None
+    if use_lib_comm and not args.no_balance and not args.no_e2e:
+        # the end-to-end leg is bound by the upload, for which equal shards are best: keep the equal shard on the host
+        import psutil
+        if psutil.virtual_memory().available > nbytes * world * 1.15 + (8 << 30):
+            h_eq = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            h_eq.copy_(d_text[:nbytes])
+            torch.cuda.synchronize(dev)
+            eq = {"h_text": h_eq, "nbytes": nbytes, "pos_base": pos_base, "r0": r0, "reads": per_rank}
     if use_lib_comm and not args.no_balance:
         # Rank 0 alone turns the gathered runs into the sketch (slot order needs one table) while the other ranks
         # are already streaming their next shard, and then everybody waits for it at the next exchange.  So rank 0
@@ -457,18 +466,24 @@ def run_ours(args):
             t = torch.tensor([e2e_reads], dtype=torch.int64, device=dev)
             dist.all_reduce(t)
             e2e_total = int(t.item())
-        e_nbytes = spec.fastq_bytes(r0, r0 + e2e_reads)
         numa = D.bind_to_gpu_numa(local)          # the pinned buffer is first touched on the GPU's own NUMA node
-        h_text = torch.empty(e_nbytes, dtype=torch.uint8, pin_memory=True)
-        h_text.copy_(d_text[:e_nbytes])
-        torch.cuda.synchronize(dev)
+        e_r0, e_pos_base = r0, pos_base
+        if eq is not None:                        # equal shards (see above); the exchange blocks are sized again for them
+            h_text, e_nbytes, e_pos_base, e_r0, e2e_reads = eq["h_text"], eq["nbytes"], eq["pos_base"], eq["r0"], eq["reads"]
+            e2e_total = world * e2e_reads
+            max_runs = D.size_exchange_blocks(sk, h_text, e_nbytes, e_pos_base, 4 * e_r0, rank == world - 1, host_text=True)
+        else:
+            e_nbytes = spec.fastq_bytes(r0, r0 + e2e_reads)
+            h_text = torch.empty(e_nbytes, dtype=torch.uint8, pin_memory=True)
+            h_text.copy_(d_text[:e_nbytes])
+            torch.cuda.synchronize(dev)
 
         def step_host():
             if world == 1:
                 return composite(sk.fastq_koc_host(h_text), False)
             # multi-GPU: every rank uploads its shard from its own pinned buffer (chunks overlapped with
             # the kernel), then the sharded path
-            return sharded_step(h_text, e_nbytes, pos_base, 4 * r0, rank == world - 1, host_text=True)[1]
+            return sharded_step(h_text, e_nbytes, e_pos_base, 4 * e_r0, rank == world - 1, host_text=True)[1]
 
         # what the host side can deliver: every rank copies its pinned shard to its GPU at the same time, nothing else
         # running (the end-to-end step cannot be faster than this copy; at N > 1 the GPUs share PCIe switches / host DRAM)
@@ -507,7 +522,8 @@ def run_ours(args):
         e2e = {"value": e2e_total * READ_LEN / 1e9 / (ms_e / 1e3), "unit": "Gbp/s",
                "h2d_bytes_per_step": int(pe.h2d_bytes // e_steps), "d2h_bytes_per_step": int(pe.d2h_bytes // e_steps),
                "bytes_source": "counted by the library per copy (mk_profile), this rank",
-               "ms_per_step": ms_e, "reads_per_gpu": e2e_reads, "numa_node_of_rank0": numa,
+               "ms_per_step": ms_e, "reads_per_gpu": e2e_reads, "shards": "equal" if (eq is not None or balance is None) else "as in the value leg",
+               "numa_node_of_rank0": numa,
                "h2d_copy_only": {"ms": ms_copy, "GBps_per_gpu": e_nbytes / 1e6 / ms_copy,
                                  "GBps_all_gpus": world * e_nbytes / 1e6 / ms_copy,
                                  "what": "all ranks copy their pinned shard to their GPU at once, max over ranks; "

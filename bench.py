@@ -426,10 +426,7 @@ def run_ours(args):
             stream_ms_per_read = sum(float(x[1]) for x in allw) / (world * per_rank)
             tail_ms = sum(waits[1:]) / (world - 1) - waits[0]      # > 0: the others wait for rank 0
             history.append({"exchange_wait_ms_per_rank": waits, "rank0_tail_ms": tail_ms})
-            d_total += int(tail_ms / stream_ms_per_read * (world - 1) / world)
-            d_total = max(0, min(d_total, per_rank * 2 // 5))
-            shares = [per_rank - d_total] + [per_rank + d_total // (world - 1)] * (world - 1)
-            shares[-1] += world * per_rank - sum(shares)
+            shares, d_total = D.balanced_shares(per_rank, world, waits, stream_ms_per_read, d_total)
             starts = [sum(shares[:q]) for q in range(world)]
             r0, r1 = starts[rank], starts[rank] + shares[rank]
             my_reads = shares[rank]

@@ -194,3 +194,19 @@ def size_exchange_blocks(sk, text, nbytes: int, pos_base: int, line_base: int, i
         if not failed:
             return cap
     raise RuntimeError("exchange block capacity did not settle")
+
+
+def balanced_shares(per_rank: int, world: int, waits_ms, stream_ms_per_read: float, moved_so_far: int = 0):
+    """Reads per rank for the sharded step when rank 0 carries the tail (slot order of the gathered sketch, statistics).
+    `waits_ms[r]` = mk_profile.exchange_wait_ms per step of rank r in steady state: the other ranks' wait minus
+    rank 0's own is what rank 0's tail costs; rank 0 gets fewer reads by what streams in that time (times
+    (world-1)/world, because the reads it gives up make the others slower), the total stays world * per_rank.
+    Returns (shares, moved): `moved` = reads taken from rank 0 so far (pass it back in to refine)."""
+    if world < 2:
+        return [per_rank], 0
+    tail_ms = sum(waits_ms[1:]) / (world - 1) - waits_ms[0]
+    moved = moved_so_far + int(tail_ms / stream_ms_per_read * (world - 1) / world)
+    moved = max(0, min(moved, per_rank * 2 // 5))
+    shares = [per_rank - moved] + [per_rank + moved // (world - 1)] * (world - 1)
+    shares[-1] += world * per_rank - sum(shares)
+    return shares, moved

@@ -154,3 +154,22 @@ def test_code_range_edges_balance_the_owners(oracle):
         assert share.max() < 1.35 / world and share.min() > 0.65 / world, (world, share)
     even = np.histogram(codes, bins=[0, 1 << 31, 1 << 32])[0] / codes.size
     assert even[0] > 0.6                                   # what equal-width ranges would have done
+
+
+def test_balanced_shares_keep_the_total_and_equalise_the_ranks():
+    """distributed.balanced_shares: rank 0 (which carries the tail of the sharded step) gets fewer reads; with the
+    shares it returns, stream time + tail of rank 0 equals the stream time of the others."""
+    from metakssd_b200 import distributed as D
+    per, ms_per_read = 40_000_000, 8.0 / 40_000_000
+    for world, tail in ((2, 0.9), (4, 1.2), (8, 1.5)):
+        waits = [0.1] + [0.1 + tail] * (world - 1)
+        shares, moved = D.balanced_shares(per, world, waits, ms_per_read)
+        assert sum(shares) == world * per and shares[0] == per - moved and min(shares) > 0
+        assert abs((shares[0] * ms_per_read + tail) - shares[1] * ms_per_read) < 1e-3
+        again, moved2 = D.balanced_shares(per, world, [0.1] * world, ms_per_read, moved)      # nothing left to correct
+        assert again == shares and moved2 == moved
+        back, moved3 = D.balanced_shares(per, world, [0.1 + tail] + [0.1] * (world - 1), ms_per_read, moved)   # over-corrected
+        assert moved3 < moved and sum(back) == world * per
+    assert D.balanced_shares(per, 1, [0.0], ms_per_read) == ([per], 0)
+    shares, moved = D.balanced_shares(per, 4, [0.0, 100.0, 100.0, 100.0], ms_per_read)        # capped at 40 % of a shard
+    assert moved == per * 2 // 5 and sum(shares) == 4 * per

@@ -242,6 +242,17 @@ int mk_set_operate(mk_ctx *ctx, const uint32_t *pan, uint64_t n_pan, const uint3
                    int n_sketches, int intersect, uint32_t **out_codes, uint64_t *out_index /* [n_sketches + 1] */);
 void mk_free(void *p);
 
+/* ---- `dist -r <ref> <qry>`: shared k-mer counts -------------------------------------------
+ * Replaces the inverted index of combco2mco() (co2mco.c:12-86) and the probe loop of mco_cbdco_nobin_dist()
+ * (command_dist.c:1031-1046) for one component: counts[q * n_ref + r] += number of codes of query sketch q
+ * (qry_codes[qry_index[q] .. qry_index[q+1])) that reference sketch r holds.  All pointers are host memory;
+ * `counts` ([n_qry * n_ref], zeroed by the caller) accumulates over the components.  qry_ctx_ct (may be NULL):
+ * queries whose code count is 0 are skipped like the reference does.  The distance table is printed by the
+ * host from counts and the two ctx_ct lists (host/mkssd_main.c, command_dist.c:1531-1680). */
+int mk_shared_counts(mk_ctx *ctx, const uint32_t *ref_codes, const uint64_t *ref_index, int n_ref,
+                     const uint32_t *qry_codes, const uint64_t *qry_index, int n_qry, const uint32_t *qry_ctx_ct,
+                     uint32_t *counts);
+
 /* ---- the multi-GPU step inside the library (NCCL over NVLink; one context per rank / GPU) -------- */
 /* mk_comm_unique_id(): 128 bytes from ncclGetUniqueId() on one rank, handed to all ranks by the host's own
  * means (MPI / torch.distributed / a file); mk_comm_init() joins the communicator (ncclCommInitRank).  NCCL is

@@ -94,7 +94,7 @@ EXPORTS = [
     "mk_synth_fasta_device", "mk_synth_build", "mk_synth_free", "mk_synth_fastq_bytes", "mk_synth_fasta_bytes",
     "mk_synth_shuf_perm", "mk_synth_shuf_id",
     "mk_comm_unique_id", "mk_comm_init", "mk_comm_destroy", "mk_comm_last_block_need", "mk_markerdb_load_sharded", "mk_fastq_koc_sharded_device",
-    "mk_fastq_koc_sharded_host", "mk_set_group", "mk_set_uniq_union", "mk_set_operate", "mk_free",
+    "mk_fastq_koc_sharded_host", "mk_set_group", "mk_set_uniq_union", "mk_set_operate", "mk_free", "mk_shared_counts",
 ]
 
 _lib = None
@@ -175,6 +175,7 @@ def load():
     L.mk_comm_unique_id.argtypes = [vp, sz]
     L.mk_comm_init.argtypes = [vp, vp, i32, i32]
     L.mk_comm_destroy.argtypes = [vp]
+    L.mk_shared_counts.argtypes = [vp, vp, vp, C.c_int, vp, vp, C.c_int, vp, vp]
     L.mk_comm_last_block_need.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.mk_markerdb_load_sharded.argtypes = [vp, i32, vp, vp, i32]
     L.mk_fastq_koc_sharded_device.argtypes = [vp, vp, sz, u64, u64, i32, u64, C.POINTER(MkSketch), vp]
@@ -538,6 +539,19 @@ class Sketcher:
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         self._ck(self._L.mk_comm_init(self._h, C.c_char_p(unique_id), rank, world))
         self.rank, self.world = rank, world
+
+    def shared_counts(self, ref_comp, qry_comp, qry_ctx_ct=None) -> np.ndarray:
+        """`dist -r`: ref_comp / qry_comp = lists over components of (codes uint32, index uint64[n+1]); returns the
+        shared k-mer counts uint32[n_qry, n_ref] (mco_cbdco_nobin_dist, command_dist.c:1031-1046)."""
+        n_ref, n_qry = int(ref_comp[0][1].size - 1), int(qry_comp[0][1].size - 1)
+        counts = np.zeros((n_qry, n_ref), dtype=np.uint32)
+        ct = None if qry_ctx_ct is None else np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
+        for (rc, ri), (qc, qi) in zip(ref_comp, qry_comp):
+            rc = np.ascontiguousarray(rc, dtype=np.uint32); ri = np.ascontiguousarray(ri, dtype=np.uint64)
+            qc = np.ascontiguousarray(qc, dtype=np.uint32); qi = np.ascontiguousarray(qi, dtype=np.uint64)
+            self._ck(self._L.mk_shared_counts(self._h, rc.ctypes.data, ri.ctypes.data, n_ref, qc.ctypes.data, qi.ctypes.data,
+                                              n_qry, None if ct is None else ct.ctypes.data, counts.ctypes.data))
+        return counts
 
     def comm_last_block_need(self) -> int:
         """Largest exchange block this rank saw in the last sharded step (valid after MK_ERR_NOMEM too)."""

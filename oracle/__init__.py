@@ -23,8 +23,9 @@ REF_BIN = os.path.join(HERE, "_ref", "metakssd")
 
 def build(force: bool = False) -> None:
     """Compile liboracle.so (and oracle/_ref/metakssd when /root/reference is present)."""
-    if force or not os.path.exists(LIB_PATH):
-        subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)      # (no-op when up to date)
     if os.path.isdir("/root/reference") and (force or not os.path.exists(REF_BIN)):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
 
@@ -291,6 +292,51 @@ def composite(ref_comp, ref_names, qry_comp, qry_name: str) -> str:
     w = lib().ko_composite_report(qry_name.encode(), names, S, C.cast(ptrs, C.c_void_p), nhits.ctypes.data, out, cap)
     del store
     return out.raw[:w].decode()
+
+
+# --------------------------------------------------------------------------- dist -r (shared k-mer counts, distance table)
+def shared_counts(ref_comp, qry_comp, qry_ctx_ct=None) -> np.ndarray:
+    """ref_comp / qry_comp: lists over components of (codes uint32, index uint64[n+1]).  Returns uint32[n_qry, n_ref]."""
+    n_ref, n_qry = ref_comp[0][1].size - 1, qry_comp[0][1].size - 1
+    counts = np.zeros((n_qry, n_ref), dtype=np.uint32)
+    qc = None if qry_ctx_ct is None else np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
+    for (rc, ri), (qcodes, qi) in zip(ref_comp, qry_comp):
+        rc = np.ascontiguousarray(rc, dtype=np.uint32); ri = np.ascontiguousarray(ri, dtype=np.uint64)
+        qcodes = np.ascontiguousarray(qcodes, dtype=np.uint32); qi = np.ascontiguousarray(qi, dtype=np.uint64)
+        f = lib().ko_shared_counts
+        f.restype = None
+        f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        f(rc.ctypes.data, ri.ctypes.data, n_ref, qcodes.ctypes.data, qi.ctypes.data, n_qry,
+          None if qc is None else qc.ctypes.data, counts.ctypes.data)
+    return counts
+
+
+def distance_out(counts, ref_ctx_ct, qry_ctx_ct, ref_names, qry_names, kmerlen, dim_rd_len, metric=0, outfields=2,
+                 correction=0, n_max=0, max_dist=1.0) -> str:
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    n_qry, n_ref = counts.shape
+    rc = np.ascontiguousarray(ref_ctx_ct, dtype=np.uint32); qc = np.ascontiguousarray(qry_ctx_ct, dtype=np.uint32)
+    rn = (C.c_char_p * n_ref)(*[n.encode() for n in ref_names]); qn = (C.c_char_p * n_qry)(*[n.encode() for n in qry_names])
+    f = lib().ko_distance_out
+    f.restype = C.c_size_t
+    f.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                  C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    args = (counts.ctypes.data, n_ref, n_qry, rc.ctypes.data, qc.ctypes.data, C.cast(rn, C.c_void_p), C.cast(qn, C.c_void_p), metric,
+            outfields, correction, n_max, float(max_dist), kmerlen, dim_rd_len)
+    need = f(*args, None, 0)
+    out = C.create_string_buffer(need + 1)
+    f(*args, C.cast(out, C.c_void_p), need)
+    return out.raw[:need].decode()
+
+
+def ref_dist_search(refdir: str, qrydir: str, outdir: str, extra=(), p: int = 1) -> str:
+    """`metakssd dist -r <refdir> -o <outdir> [extra] <qrydir>` with the reference binary; returns distance.out.
+    The first use of a co directory as -r makes the reference write its inverted index into it (mco.index.N is
+    2^32 x 8 bytes = 32 GiB per component, co2mco.c:17-67): minutes of time and 32 GiB of disk per component."""
+    import shutil
+    shutil.rmtree(outdir, ignore_errors=True)
+    run_ref(["dist", "-r", refdir, "-o", outdir, "-p", str(p)] + list(extra) + [qrydir])
+    return open(os.path.join(outdir, "distance.out")).read()
 
 
 # --------------------------------------------------------------------------- sketch directories

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <stdio.h>
+#include <math.h>
 #include "mkssd_synth.h"
 
 typedef unsigned long long u64;
@@ -658,6 +659,123 @@ size_t ko_composite_report(const char *qry_name, const char *const *ref_names, i
 }
 
 /* ---------------- synthetic data (thin wrappers so ctypes can reach the header) ---------- */
+/* =================================================================================================
+ * `dist -r <ref> <qry>`: shared k-mer counts of every query sketch with every reference sketch and the
+ * distance table.
+ *   ko_shared_counts()  mco_cbdco_nobin_dist() core, /root/reference/command_dist.c:1031-1046, with the inverted
+ *                       index of combco2mco() (co2mco.c:12-86) replaced by what it encodes: for every code the
+ *                       reference sketches that hold it.  counts[q * n_ref + r] += 1 for every code of query q
+ *                       that reference r holds (one component per call, counts accumulate over components).
+ *   ko_distance_out()   dist_print_nobin() + output_ctrl(), command_dist.c:1531-1680: header, per query either
+ *                       every reference in order or the N with the largest metric (insertion order of :1595-1604),
+ *                       lines farther than max_dist dropped.
+ * ================================================================================================= */
+static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }
+
+void ko_shared_counts(const uint32_t *ref_codes, const size_t *ref_index, int n_ref, const uint32_t *qry_codes,
+                      const size_t *qry_index, int n_qry, const uint32_t *qry_ctx_ct, uint32_t *counts)
+{
+    /* (code, ref) pairs sorted by code = the rows of the reference's mco index */
+    size_t R = ref_index[n_ref];
+    uint64_t *pair = malloc(sizeof(uint64_t) * (R ? R : 1));
+    size_t m = 0;
+    for (int r = 0; r < n_ref; r++)
+        for (size_t i = ref_index[r]; i < ref_index[r + 1]; i++) pair[m++] = ((uint64_t)ref_codes[i] << 32) | (uint32_t)r;
+    qsort(pair, m, sizeof(uint64_t), cmp_u64);
+    for (int q = 0; q < n_qry; q++) {
+        if (qry_ctx_ct && qry_ctx_ct[q] == 0) continue;                      /* command_dist.c:1033 */
+        for (size_t i = qry_index[q]; i < qry_index[q + 1]; i++) {
+            const uint64_t key = (uint64_t)qry_codes[i] << 32;
+            size_t lo = 0, hi = m;
+            while (lo < hi) { size_t mid = (lo + hi) >> 1; if (pair[mid] < key) lo = mid + 1; else hi = mid; }
+            for (; lo < m && (pair[lo] >> 32) == qry_codes[i]; lo++) counts[(size_t)q * n_ref + (uint32_t)pair[lo]]++;
+        }
+    }
+    free(pair);
+}
+
+typedef struct { int metric, outfields, correction, n_max; double max_dist; int kmerlen, dim_rd_len; } ko_dist_opt;
+
+/* one line of output_ctrl() (command_dist.c:1637-1680); returns its length, 0 if the line is dropped */
+static int ko_dist_line(char *line, size_t cap, const ko_dist_opt *o, const char *qname, const char *rname, unsigned X,
+                        unsigned Y, unsigned XnY, double n_cmp)
+{
+    double rs = 0;
+    if (o->correction) {
+        unsigned a = X - XnY, b = Y - XnY;
+        double pa = 1 - pow((1 - 1 / pow(4, (o->kmerlen - o->dim_rd_len))), a);
+        double pb = 1 - pow((1 - 1 / pow(4, (o->kmerlen - o->dim_rd_len))), b);
+        rs = pa * pb * (a + b) / (pa + pb - 2 * pa * pb);
+    }
+    unsigned tmp = o->metric == 0 ? X + Y - XnY : (X < Y ? X : Y);
+    double metric = ((double)XnY - rs) / tmp;
+    double dist = log(o->metric == 0 ? 1 / (2 * metric) + 0.5 : 1 / metric) / o->kmerlen;
+    if (dist > 1) dist = 1;
+    if (dist > o->max_dist) return 0;
+    int len = snprintf(line, cap, "%s\t%s\t%u-%u|%u|%u\t%.6lf\t%.6lf", qname, rname, XnY, (unsigned)rs, X, Y, metric, dist);
+    if (o->outfields > 0) {
+        double sd = pow(metric * (1 - metric) / tmp, 0.5);
+        double pv = 0.5 * erfc(metric / sd * pow(0.5, 0.5));
+        len += snprintf(line + len, cap - len, "\t%E\t%E", pv, pv * n_cmp);
+        if (o->outfields > 1) {
+            double m1 = metric - 1.96 * sd, m2 = metric + 1.96 * sd;
+            double d1 = log(o->metric == 0 ? 1 / (2 * m2) + 0.5 : 1 / m2) / o->kmerlen;
+            double d2 = log(o->metric == 0 ? 1 / (2 * m1) + 0.5 : 1 / m1) / o->kmerlen;
+            len += snprintf(line + len, cap - len, "\t[%.6lf,%.6lf]\t[%.6lf,%.6lf]", m1, m2, d1, d2);
+        }
+    }
+    len += snprintf(line + len, cap - len, "\n");
+    return len;
+}
+
+size_t ko_distance_out(const uint32_t *counts, int n_ref, int n_qry, const uint32_t *ref_ctx_ct, const uint32_t *qry_ctx_ct,
+                       const char *const *ref_names, const char *const *qry_names, int metric, int outfields,
+                       int correction, int n_max, double max_dist, int kmerlen, int dim_rd_len, char *out, size_t cap)
+{
+    static const char *hdr[2][3] = {{"Jaccard\tMashD", "P-value(J)\tFDR(J)", "Jaccard_CI\tMashD_CI"},
+                                    {"ContainmentM\tAafD", "P-value(C)\tFDR(C)", "ContainmentM_CI\tAafD_CI"}};
+    ko_dist_opt o = {metric, outfields, correction, n_max, max_dist, kmerlen, dim_rd_len};
+    size_t w = 0;
+    char line[2048];
+#define KO_PUT(str, n) do { if (out && w + (n) <= cap) memcpy(out + w, (str), (n)); w += (n); } while (0)
+    int n = snprintf(line, sizeof line, "Qry\tRef\tShared_k|Ref_s|Qry_s");
+    for (int i = 0; i <= outfields; i++) n += snprintf(line + n, sizeof line - n, "\t%s", hdr[metric][i]);
+    n += snprintf(line + n, sizeof line - n, "\n");
+    KO_PUT(line, (size_t)n);
+    const double n_cmp = (double)((unsigned)n_ref * (unsigned)n_qry);          /* cmprsn_num: unsigned product, :1560 */
+    typedef struct { double metric; int rid; } best_t;
+    best_t *best = malloc(sizeof(best_t) * (size_t)(n_max + 2));
+    for (int q = 0; q < n_qry; q++) {
+        const unsigned Y = qry_ctx_ct[q];
+        const uint32_t *row = counts + (size_t)q * n_ref;
+        if (n_max) {
+            for (int i = 0; i < n_max; i++) { best[i].metric = 0; best[i].rid = -1; }
+            for (int r = 0; r < n_ref; r++) {
+                unsigned X = ref_ctx_ct[r], XnY = row[r];
+                double m = metric == 1 ? (double)XnY / (X < Y ? X : Y) : (double)XnY / (X + Y - XnY);
+                for (int i = n_max - 1; i >= 0; i--) {
+                    if (m > best[i].metric) { best[i + 1] = best[i]; best[i].metric = m; best[i].rid = r; }
+                    else break;
+                }
+            }
+            for (int i = 0; i < n_max; i++) {
+                if (best[i].rid < 0) continue;
+                int len = ko_dist_line(line, sizeof line, &o, qry_names[q], ref_names[best[i].rid], ref_ctx_ct[best[i].rid], Y,
+                                       row[best[i].rid], n_cmp);
+                if (len > 1) KO_PUT(line, (size_t)len);
+            }
+        } else {
+            for (int r = 0; r < n_ref; r++) {
+                int len = ko_dist_line(line, sizeof line, &o, qry_names[q], ref_names[r], ref_ctx_ct[r], Y, row[r], n_cmp);
+                if (len > 1) KO_PUT(line, (size_t)len);
+            }
+        }
+    }
+#undef KO_PUT
+    free(best);
+    return w;
+}
+
 int ko_synth_params(mks_params *P, uint64_t seed, uint32_t n_species, uint32_t genome_len, uint32_t read_len,
                     uint32_t **cdf32, uint32_t **species)
 {

@@ -156,3 +156,29 @@ def set_case():
             groups.append("%d\tsp%d" % (taxids[s], s))
     order = rng.permutation(len(genomes))
     return (11, 6, 3, 1234), [genomes[i] for i in order], [groups[i] for i in order]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# `dist -r <ref> <qry>` (shared k-mer counts + distance table); vectors in tests/golden/reference_vectors_r2b.npz
+# (tests/golden/make_golden_r2b.py).  The reference orders the files of a sketch directory by a time-seeded shuffle,
+# so the vectors also hold the order of the names; tests rebuild the directories in that order.
+DIST_SEARCH_OPTIONS = {
+    "default": [],
+    "containment": ["-M", "1"],
+    "distance_only": ["-O", "0"],
+    "with_qvalues": ["-O", "1"],
+    "nearest3": ["-N", "3"],
+    "nearest2_containment": ["-N", "2", "-M", "1"],
+    "max_dist": ["-D", "0.08"],
+    "corrected": ["--correction", "1"],
+}
+
+
+def dist_search_case():
+    """((k, subk, L, shuf_seed), {name: genome text}, ref names, qry genome names, reads text): the 25 strain genomes of
+    set_case() — 17 of them the reference database, 12 queries (4 also in the database) and one read sample."""
+    geo, genomes, _ = set_case()
+    named = {"g%02d.fasta" % i: g for i, g in enumerate(genomes)}
+    names = sorted(named)
+    S = O.synth(79, 10, 180_000, 150)
+    return geo, named, names[:17], names[13:], bytes(S.fastq(0, 20_000))

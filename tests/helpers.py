@@ -26,3 +26,26 @@ def markerdb_from_sketches(species_codes):
         out.append(keep)
         index.append(index[-1] + keep.size)
     return (np.concatenate(out) if out else np.empty(0, np.uint32)), np.array(index, dtype=np.uint64)
+
+
+def dist_search_world(oracle, gold):
+    """The sketches of golden_cases.dist_search_case() in the file order the reference gave its directories
+    (tests/golden/reference_vectors_r2b.npz): (p, perm, ref names, ref (codes, index), ref ctx_ct, qry names, qry (codes, index),
+    qry ctx_ct), one component (L3K11)."""
+    import golden_cases as G
+    import numpy as np
+    (k, subk, L, seed), named, _, _, _ = G.dist_search_case()
+    p = oracle.params(k, subk, L)
+    _, perm = oracle.make_shuf(seed, k, subk, L)
+
+    def side(names):
+        sk = [oracle.fasta_co(p, perm, named[n]).components(p)[0][0] for n in names]
+        index = np.zeros(len(sk) + 1, dtype=np.uint64)
+        index[1:] = np.cumsum([s.size for s in sk])
+        return (np.concatenate(sk).astype(np.uint32), index), np.array([s.size for s in sk], dtype=np.uint32)
+
+    ref_names = [str(n) for n in gold["ref/names"]]
+    qry_names = [str(n) for n in gold["qry/names"]]
+    ref, ref_ct = side(ref_names)
+    qry, qry_ct = side(qry_names)
+    return p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct

@@ -76,3 +76,42 @@ def test_set_pipeline_golden(oracle, gold):
     assert np.array_equal(mc, gold["set/markerdb/combco.0"]) and np.array_equal(mi, gold["set/markerdb/index.0"])
     sc, si = oracle.set_operate(u, pc, pi, False)
     assert sc.size + mc.size == pc.size
+
+
+# ---- `dist -r`: shared k-mer counts and the distance table (tests/golden/reference_vectors_r2b.npz) ----------------
+GOLD_B = os.path.join(os.path.dirname(__file__), "golden", "reference_vectors_r2b.npz")
+
+
+def _opts(flags):
+    o = dict(metric=0, outfields=2, correction=0, n_max=0, max_dist=1.0)
+    key = {"-M": "metric", "-O": "outfields", "-N": "n_max", "--correction": "correction"}
+    for a, b in zip(flags[::2], flags[1::2]):
+        if a == "-D":
+            o["max_dist"] = float(b)
+        else:
+            o[key[a]] = int(b)
+    return o
+
+
+def test_dist_search_golden(oracle):
+    """ko_shared_counts / ko_distance_out against `metakssd dist -r ref qry` of the reference binary: the count matrix
+    it keeps with --keepskf and distance.out for eight option sets, byte for byte."""
+    from helpers import dist_search_world
+    gold = np.load(GOLD_B)
+    p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct = dist_search_world(oracle, gold)
+    assert np.array_equal(ref_ct, gold["ref/ctx_ct"]) and np.array_equal(qry_ct, gold["qry/ctx_ct"])
+    counts = oracle.shared_counts([ref], [qry], qry_ct)
+    assert np.array_equal(counts, gold["sharedk_ct"])
+    assert counts.max() > 30 and (counts > 0).sum() > 100
+    for name, flags in G.DIST_SEARCH_OPTIONS.items():
+        txt = oracle.distance_out(counts, ref_ct, qry_ct, ref_names, qry_names, 2 * p.k, 2 * p.drlevel, **_opts(flags))
+        assert txt == str(gold["out/" + name]), name
+    # a read sample sketched with -A as the query (counts ignored, codes as they are on disk)
+    (k, subk, L, seed), _, _, _, reads = G.dist_search_case()
+    sk = oracle.fastq_koc(p, perm, np.frombuffer(reads, np.uint8)).components(p)[0][0]
+    assert np.array_equal(sk, gold["qryA/combco.0"])
+    qa = (sk.astype(np.uint32), np.array([0, sk.size], dtype=np.uint64))
+    ca = oracle.shared_counts([ref], [qa], gold["qryA/ctx_ct"])
+    assert np.array_equal(ca, gold["sharedk_ct_A"])
+    txt = oracle.distance_out(ca, ref_ct, gold["qryA/ctx_ct"], ref_names, ["reads.fq"], 2 * p.k, 2 * p.drlevel)
+    assert txt == str(gold["outA/default"])

@@ -20,6 +20,7 @@
  */
 #define _GNU_SOURCE
 #include <errno.h>
+#include <math.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -127,9 +128,169 @@ static int cmd_shuffle(int argc, char **argv)
 }
 
 /* ---- dist ------------------------------------------------------------------------------------ */
+/* ---- dist -r <ref> -o <out> <qry>: shared k-mer counts + distance table ---------------------------------
+ * mco_cbdco_nobin_dist() (command_dist.c:902-1079): the counts come from mk_shared_counts() (one call per component),
+ * the table is dist_print_nobin() / output_ctrl() (command_dist.c:1531-1680) — four integers per pair through the same
+ * libm expressions and printf formats.  <ref> is a sketch directory (cofiles.stat, or mcofiles.stat next to the combco
+ * files when the reference has already indexed it in place); the reference's own 32 GiB mco.index.N is neither
+ * needed nor written. */
+typedef struct { unsigned int shuf_id; int kmerlen, dim_rd_len, comp_num, infile_num; } mco_dstat_t;   /* command_dist.h:67-75 */
+static mk_ctx *plain_ctx(const co_dstat_t *st);
+typedef struct { int metric, outfields, correction, n_max, keep; double max_dist; } search_opt;
+
+static int dist_line(char *line, size_t cap, const search_opt *o, int kmerlen, int dim_rd_len, const char *qname,
+                     const char *rname, unsigned X, unsigned Y, unsigned XnY, double n_cmp)
+{
+#define GET_METRIC(M, Y_) ((M) == 0 ? 1 / (2 * (Y_)) + 0.5 : 1 / (Y_))
+    double rs = 0;
+    if (o->correction) {
+        unsigned a = X - XnY, b = Y - XnY;
+        double pa = 1 - pow((1 - 1 / pow(4, (kmerlen - dim_rd_len))), a);
+        double pb = 1 - pow((1 - 1 / pow(4, (kmerlen - dim_rd_len))), b);
+        rs = pa * pb * (a + b) / (pa + pb - 2 * pa * pb);
+    }
+    unsigned tmp = o->metric == 0 ? X + Y - XnY : (X < Y ? X : Y);
+    double metric = ((double)XnY - rs) / tmp;
+    double dist = log(GET_METRIC(o->metric, metric)) / kmerlen;
+    if (dist > 1) dist = 1;
+    if (dist > o->max_dist) return 0;
+    int len = snprintf(line, cap, "%s\t%s\t%u-%u|%u|%u\t%.6lf\t%.6lf", qname, rname, XnY, (unsigned)rs, X, Y, metric, dist);
+    if (o->outfields > 0) {
+        double sd = pow(metric * (1 - metric) / tmp, 0.5);
+        double pv = 0.5 * erfc(metric / sd * pow(0.5, 0.5));
+        len += snprintf(line + len, cap - len, "\t%E\t%E", pv, pv * n_cmp);
+        if (o->outfields > 1) {
+            double m1 = metric - 1.96 * sd, m2 = metric + 1.96 * sd;
+            double d1 = log(GET_METRIC(o->metric, m2)) / kmerlen, d2 = log(GET_METRIC(o->metric, m1)) / kmerlen;
+            len += snprintf(line + len, cap - len, "\t[%.6lf,%.6lf]\t[%.6lf,%.6lf]", m1, m2, d1, d2);
+        }
+    }
+    len += snprintf(line + len, cap - len, "\n");
+    return len;
+#undef GET_METRIC
+}
+
+static int dist_search(const char *refdir, const char *qrydir, const char *outdir, const search_opt *o)
+{
+    char path[PATHLEN * 2];
+    size_t n;
+    /* reference side: mcofiles.stat if the reference binary has indexed the directory, else cofiles.stat */
+    mco_dstat_t R;
+    unsigned int *r_ct;
+    char (*r_names)[PATHLEN];
+    snprintf(path, sizeof path, "%s/mcofiles.stat", refdir);
+    struct stat sb;
+    char *raw;
+    if (stat(path, &sb) == 0) {
+        raw = slurp(path, &n);
+        memcpy(&R, raw, sizeof R);
+        r_ct = (unsigned int *)(raw + sizeof R);
+    } else {
+        snprintf(path, sizeof path, "%s/cofiles.stat", refdir);
+        raw = slurp(path, &n);
+        co_dstat_t c;
+        memcpy(&c, raw, sizeof c);
+        R.shuf_id = c.shuf_id; R.kmerlen = c.kmerlen; R.dim_rd_len = c.dim_rd_len; R.comp_num = c.comp_num; R.infile_num = c.infile_num;
+        r_ct = (unsigned int *)(raw + sizeof c);
+    }
+    r_names = (char (*)[PATHLEN])((char *)r_ct + (size_t)R.infile_num * 4);
+    snprintf(path, sizeof path, "%s/cofiles.stat", qrydir);
+    char *qraw = slurp(path, &n);
+    co_dstat_t Q;
+    memcpy(&Q, qraw, sizeof Q);
+    unsigned int *q_ct = (unsigned int *)(qraw + sizeof Q);
+    char (*q_names)[PATHLEN] = (char (*)[PATHLEN])((char *)q_ct + (size_t)Q.infile_num * 4);
+    if (Q.shuf_id != R.shuf_id) {
+        fprintf(stderr, "metakssd-b200: qry shuf_id: %d not match ref shuf_id: %d\n", (int)Q.shuf_id, (int)R.shuf_id);
+        exit(1);
+    }
+    if (Q.comp_num != R.comp_num) {
+        fprintf(stderr, "metakssd-b200: qry comp_num: %d not match ref comp_num: %d\n", Q.comp_num, R.comp_num);
+        exit(1);
+    }
+    const int n_ref = R.infile_num, n_qry = Q.infile_num;
+    if (o->n_max > 1024 || o->n_max > n_ref) {
+        fprintf(stderr, "metakssd-b200: neighborN_max %d should smaller than NREF %d and ref_num %d\n", o->n_max, 1024, n_ref);
+        exit(1);
+    }
+    g_t0 = now_s();
+    co_dstat_t geo = Q;
+    mk_ctx *ctx = plain_ctx(&geo);
+    phase("mk_ctx_create");
+    uint32_t *counts = calloc((size_t)n_ref * (size_t)n_qry, sizeof *counts);
+    if (!counts) die("out of memory for the shared k-mer count matrix", NULL);
+    for (int c = 0; c < R.comp_num; c++) {
+        size_t b;
+        snprintf(path, sizeof path, "%s/combco.%d", refdir, c);
+        if (stat(path, &sb)) die("the reference directory holds no combco files (a bare mco index is not read)", refdir);
+        uint32_t *rc = slurp(path, &b);
+        snprintf(path, sizeof path, "%s/combco.index.%d", refdir, c);
+        uint64_t *ri = slurp(path, &b);
+        snprintf(path, sizeof path, "%s/combco.%d", qrydir, c);
+        uint32_t *qc = slurp(path, &b);
+        snprintf(path, sizeof path, "%s/combco.index.%d", qrydir, c);
+        uint64_t *qi = slurp(path, &b);
+        ck(ctx, mk_shared_counts(ctx, rc, ri, n_ref, qc, qi, n_qry, q_ct, counts), "mk_shared_counts");
+        free(rc); free(ri); free(qc); free(qi);
+    }
+    phase("shared k-mer counts");
+    mkdir(outdir, 0700);
+    if (o->keep) {
+        snprintf(path, sizeof path, "%s/sharedk_ct.dat", outdir);
+        FILE *fk = fopen(path, "wb");
+        if (!fk || fwrite(counts, sizeof *counts, (size_t)n_ref * (size_t)n_qry, fk) != (size_t)n_ref * (size_t)n_qry) die("cannot write", path);
+        fclose(fk);
+    }
+    /* distance.out (dist_print_nobin(), command_dist.c:1531-1634) */
+    static const char *hdr[2][3] = {{"Jaccard\tMashD", "P-value(J)\tFDR(J)", "Jaccard_CI\tMashD_CI"},
+                                    {"ContainmentM\tAafD", "P-value(C)\tFDR(C)", "ContainmentM_CI\tAafD_CI"}};
+    snprintf(path, sizeof path, "%s/distance.out", outdir);
+    FILE *f = fopen(path, "w");
+    if (!f) die("cannot write", path);
+    fprintf(f, "Qry\tRef\tShared_k|Ref_s|Qry_s");
+    for (int i = 0; i <= o->outfields; i++) fprintf(f, "\t%s", hdr[o->metric][i]);
+    fprintf(f, "\n");
+    const double n_cmp = (double)(long long)((unsigned)n_ref * (unsigned)n_qry);     /* outfield.cmprsn_num, :1560 */
+    typedef struct { double metric; int rid; } best_t;
+    best_t *best = malloc(sizeof(best_t) * (size_t)(o->n_max + 2));
+    char line[2048];
+    for (int q = 0; q < n_qry; q++) {
+        const unsigned Y = q_ct[q];
+        const uint32_t *row = counts + (size_t)q * (size_t)n_ref;
+        if (o->n_max) {                       /* the N references with the largest metric, ties by insertion (:1586-1605) */
+            for (int i = 0; i < o->n_max; i++) { best[i].metric = 0; best[i].rid = -1; }
+            for (int r = 0; r < n_ref; r++) {
+                unsigned X = r_ct[r], XnY = row[r];
+                double m = o->metric == 1 ? (double)XnY / (X < Y ? X : Y) : (double)XnY / (X + Y - XnY);
+                for (int i = o->n_max - 1; i >= 0; i--) {
+                    if (m > best[i].metric) { best[i + 1] = best[i]; best[i].metric = m; best[i].rid = r; }
+                    else break;
+                }
+            }
+            for (int i = 0; i < o->n_max; i++) {
+                if (best[i].rid < 0) continue;
+                int len = dist_line(line, sizeof line, o, Q.kmerlen, Q.dim_rd_len, q_names[q], r_names[best[i].rid],
+                                    r_ct[best[i].rid], Y, row[best[i].rid], n_cmp);
+                if (len > 1) fwrite(line, 1, (size_t)len, f);
+            }
+        } else {
+            for (int r = 0; r < n_ref; r++) {
+                int len = dist_line(line, sizeof line, o, Q.kmerlen, Q.dim_rd_len, q_names[q], r_names[r], r_ct[r], Y, row[r], n_cmp);
+                if (len > 1) fwrite(line, 1, (size_t)len, f);
+            }
+        }
+    }
+    fclose(f);
+    phase("distance.out");
+    mk_ctx_destroy(ctx);
+    free(best); free(counts); free(raw); free(qraw);
+    return 0;
+}
+
 static int cmd_dist(int argc, char **argv)
 {
-    const char *shuf = NULL, *outdir = "./", *pipecmd = "";
+    const char *shuf = NULL, *outdir = "./", *pipecmd = "", *refpath = NULL;
+    search_opt so = {0, 2, 0, 0, 0, 1.0};      /* command_dist_wrapper.c:83-92: Jaccard, all fields, every reference, D <= 1 */
     bool abundance = false, dedup = false;
     int kmerqlty = 0, kmerocrs = 1;            /* command_dist_wrapper.c:79-80 */
     char **inputs = malloc(sizeof(char *) * (size_t)(argc + 1));
@@ -141,6 +302,13 @@ static int cmd_dist(int argc, char **argv)
         else if (!strcmp(argv[i], "-P") && i + 1 < argc) pipecmd = argv[++i];
         else if (!strcmp(argv[i], "-A")) abundance = true;
         else if (!strcmp(argv[i], "-u")) dedup = true;
+        else if (!strcmp(argv[i], "-r") && i + 1 < argc) refpath = argv[++i];
+        else if (!strcmp(argv[i], "-M") && i + 1 < argc) so.metric = atoi(argv[++i]) ? 1 : 0;
+        else if (!strcmp(argv[i], "-O") && i + 1 < argc) { so.outfields = atoi(argv[++i]); if (so.outfields < 0 || so.outfields > 2) die("-O takes 0, 1 or 2", NULL); }
+        else if (!strcmp(argv[i], "-N") && i + 1 < argc) so.n_max = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "-D") && i + 1 < argc) so.max_dist = atof(argv[++i]);
+        else if (!strcmp(argv[i], "--correction") && i + 1 < argc) so.correction = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--keepskf")) so.keep = 1;
         else if (!strcmp(argv[i], "-Q") && i + 1 < argc) kmerqlty = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) {        /* clamped to 1..7 like command_dist_wrapper.c:169-179 */
             int v = atoi(argv[++i]);
@@ -150,6 +318,10 @@ static int cmd_dist(int argc, char **argv)
         }
         else if (argv[i][0] == '-') die("option not on the hot path", argv[i]);
         else inputs[n_in++] = argv[i];
+    }
+    if (refpath) {            /* database search: the query is a sketch directory (command_dist.c:152-171) */
+        if (n_in != 1) die("dist -r takes one query sketch directory", NULL);
+        return dist_search(refpath, inputs[0], outdir, &so);
     }
     if (!shuf) die("-L <file.shuf> is required", NULL);
     if (!n_in) die("no input sequence files", NULL);

@@ -289,10 +289,14 @@ class Sketcher:
     def __init__(self, perm: np.ndarray, k: int, subk: int, drlevel: int, device: int = 0):
         self._L = load()
         self._h = C.c_void_p()
-        perm = np.ascontiguousarray(perm, dtype=np.int32)
-        if perm.size != 1 << (4 * subk):
-            raise ValueError("permutation must have 16^subk entries")
-        rc = self._L.mk_ctx_create(C.byref(self._h), perm.ctypes.data, k, subk, drlevel, device)
+        if perm is None:          # a context without pass-set tables: composite, set operations, dist -r
+            ptr = None
+        else:
+            perm = np.ascontiguousarray(perm, dtype=np.int32)
+            if perm.size != 1 << (4 * subk):
+                raise ValueError("permutation must have 16^subk entries")
+            ptr = perm.ctypes.data
+        rc = self._L.mk_ctx_create(C.byref(self._h), ptr, k, subk, drlevel, device)
         if rc != MK_OK:
             self._h = C.c_void_p()
             raise MkError(rc, self._L.mk_strerror(rc).decode())

@@ -136,7 +136,7 @@ static int cmd_shuffle(int argc, char **argv)
  * needed nor written. */
 typedef struct { unsigned int shuf_id; int kmerlen, dim_rd_len, comp_num, infile_num; } mco_dstat_t;   /* command_dist.h:67-75 */
 static mk_ctx *plain_ctx(const co_dstat_t *st);
-typedef struct { int metric, outfields, correction, n_max, keep; double max_dist; } search_opt;
+typedef struct { int metric, outfields, correction, n_max, keep; double max_dist; const char *dump_ref; } search_opt;
 
 static int dist_line(char *line, size_t cap, const search_opt *o, int kmerlen, int dim_rd_len, const char *qname,
                      const char *rname, unsigned X, unsigned Y, unsigned XnY, double n_cmp)
@@ -168,6 +168,57 @@ static int dist_line(char *line, size_t cap, const search_opt *o, int kmerlen, i
     len += snprintf(line + len, cap - len, "\n");
     return len;
 #undef GET_METRIC
+}
+
+/* One component of a database the reference built (`dist -L x.shuf -r <genomes> -o <db>`: only mco files are left):
+ * mco.index.<c> holds, for every code s = 0 .. 2^32-1, the END offset of row s in mco.<c>, the list of references
+ * that hold code s (combco2mco(), co2mco.c:56-79; COMPONENT_SZ = 8, global_basic.h:36).  Turned back into what
+ * mk_shared_counts() takes: every reference's codes (ascending) and the index over the references.  One sequential
+ * pass over the 32 GiB index file. */
+static void read_mco_component(const char *dir, int c, int n_ref, uint32_t **codes_out, uint64_t **index_out)
+{
+    char path[PATHLEN * 2];
+    size_t gbytes;
+    snprintf(path, sizeof path, "%s/mco.%d", dir, c);
+    uint32_t *gid = slurp(path, &gbytes);
+    const uint64_t G = gbytes / 4;
+    uint32_t *code_of = malloc((size_t)(G ? G : 1) * 4);           /* code of every (code, reference) pair, in file order */
+    snprintf(path, sizeof path, "%s/mco.index.%d", dir, c);
+    FILE *f = fopen(path, "rb");
+    if (!f) die("cannot open", path);
+    const size_t CH = (size_t)8 << 20;                             /* entries per read */
+    uint64_t *buf = malloc(CH * 8);
+    if (!code_of || !buf) die("out of memory reading", path);
+    uint64_t s = 0, prev = 0;
+    for (;;) {
+        size_t got = fread(buf, 8, CH, f);
+        if (!got) break;
+        for (size_t i = 0; i < got; i++, s++) {
+            const uint64_t end = buf[i];
+            if (end != prev) {
+                if (end < prev || end > G) die("malformed mco index", path);
+                for (uint64_t g = prev; g < end; g++) code_of[g] = (uint32_t)s;
+                prev = end;
+            }
+        }
+    }
+    fclose(f);
+    free(buf);
+    if (prev != G) die("mco index and mco file disagree under", dir);
+    if (n_ref <= 0) die("no reference sketches in", dir);
+    uint64_t *index = calloc((size_t)n_ref + 1, 8);
+    for (uint64_t g = 0; g < G; g++) {
+        if (gid[g] >= (uint32_t)n_ref) die("reference id out of range in", path);
+        index[gid[g] + 1]++;
+    }
+    for (int r = 0; r < n_ref; r++) index[r + 1] += index[r];
+    uint64_t *pos = malloc(((size_t)n_ref + 1) * 8);
+    for (int r = 0; r < n_ref; r++) pos[r] = index[r];
+    uint32_t *codes = malloc((size_t)(G ? G : 1) * 4);
+    for (uint64_t g = 0; g < G; g++) codes[pos[gid[g]]++] = code_of[g];      /* codes ascend inside every reference */
+    free(pos); free(code_of); free(gid);
+    *codes_out = codes;
+    *index_out = index;
 }
 
 static int dist_search(const char *refdir, const char *qrydir, const char *outdir, const search_opt *o)
@@ -214,6 +265,36 @@ static int dist_search(const char *refdir, const char *qrydir, const char *outdi
         exit(1);
     }
     g_t0 = now_s();
+    if (o->dump_ref) {          /* no device needed: write the reference side back as combco files + cofiles.stat and leave */
+        mkdir(o->dump_ref, 0777);
+        co_dstat_t st;
+        memset(&st, 0, sizeof st);
+        st.shuf_id = R.shuf_id; st.kmerlen = R.kmerlen; st.dim_rd_len = R.dim_rd_len; st.comp_num = R.comp_num; st.infile_num = n_ref;
+        for (int r = 0; r < n_ref; r++) st.all_ctx_ct += r_ct[r];
+        for (int c = 0; c < R.comp_num; c++) {
+            uint32_t *rc;
+            uint64_t *ri;
+            read_mco_component(refdir, c, n_ref, &rc, &ri);
+            snprintf(path, sizeof path, "%s/combco.%d", o->dump_ref, c);
+            FILE *fo = fopen(path, "wb");
+            if (!fo || fwrite(rc, 4, ri[n_ref], fo) != ri[n_ref]) die("cannot write", path);
+            fclose(fo);
+            snprintf(path, sizeof path, "%s/combco.index.%d", o->dump_ref, c);
+            fo = fopen(path, "wb");
+            if (!fo || fwrite(ri, 8, (size_t)n_ref + 1, fo) != (size_t)n_ref + 1) die("cannot write", path);
+            fclose(fo);
+            free(rc); free(ri);
+        }
+        snprintf(path, sizeof path, "%s/cofiles.stat", o->dump_ref);
+        FILE *fo = fopen(path, "wb");
+        if (!fo) die("cannot write", path);
+        fwrite(&st, sizeof st, 1, fo);
+        fwrite(r_ct, 4, (size_t)n_ref, fo);
+        fwrite(r_names, PATHLEN, (size_t)n_ref, fo);
+        fclose(fo);
+        phase("dump reference side");
+        return 0;
+    }
     co_dstat_t geo = Q;
     mk_ctx *ctx = plain_ctx(&geo);
     phase("mk_ctx_create");
@@ -221,11 +302,17 @@ static int dist_search(const char *refdir, const char *qrydir, const char *outdi
     if (!counts) die("out of memory for the shared k-mer count matrix", NULL);
     for (int c = 0; c < R.comp_num; c++) {
         size_t b;
+        uint32_t *rc;
+        uint64_t *ri;
         snprintf(path, sizeof path, "%s/combco.%d", refdir, c);
-        if (stat(path, &sb)) die("the reference directory holds no combco files (a bare mco index is not read)", refdir);
-        uint32_t *rc = slurp(path, &b);
-        snprintf(path, sizeof path, "%s/combco.index.%d", refdir, c);
-        uint64_t *ri = slurp(path, &b);
+        if (stat(path, &sb) == 0) {
+            rc = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.index.%d", refdir, c);
+            ri = slurp(path, &b);
+        } else {                              /* a database built by the reference: only its inverted index is there */
+            read_mco_component(refdir, c, n_ref, &rc, &ri);
+            phase("read mco index");
+        }
         snprintf(path, sizeof path, "%s/combco.%d", qrydir, c);
         uint32_t *qc = slurp(path, &b);
         snprintf(path, sizeof path, "%s/combco.index.%d", qrydir, c);
@@ -290,7 +377,7 @@ static int dist_search(const char *refdir, const char *qrydir, const char *outdi
 static int cmd_dist(int argc, char **argv)
 {
     const char *shuf = NULL, *outdir = "./", *pipecmd = "", *refpath = NULL;
-    search_opt so = {0, 2, 0, 0, 0, 1.0};      /* command_dist_wrapper.c:83-92: Jaccard, all fields, every reference, D <= 1 */
+    search_opt so = {0, 2, 0, 0, 0, 1.0, NULL};      /* command_dist_wrapper.c:83-92: Jaccard, all fields, every reference, D <= 1 */
     bool abundance = false, dedup = false;
     int kmerqlty = 0, kmerocrs = 1;            /* command_dist_wrapper.c:79-80 */
     char **inputs = malloc(sizeof(char *) * (size_t)(argc + 1));
@@ -309,6 +396,7 @@ static int cmd_dist(int argc, char **argv)
         else if (!strcmp(argv[i], "-D") && i + 1 < argc) so.max_dist = atof(argv[++i]);
         else if (!strcmp(argv[i], "--correction") && i + 1 < argc) so.correction = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--keepskf")) so.keep = 1;
+        else if (!strcmp(argv[i], "--dump-ref") && i + 1 < argc) so.dump_ref = argv[++i];   /* (tool: the reference side as a sketch directory) */
         else if (!strcmp(argv[i], "-Q") && i + 1 < argc) kmerqlty = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) {        /* clamped to 1..7 like command_dist_wrapper.c:169-179 */
             int v = atoi(argv[++i]);

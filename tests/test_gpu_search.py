@@ -107,3 +107,27 @@ def test_cli_refuses_what_the_reference_refuses(lib_built, oracle, tmp_path):
     open(os.path.join(qd, "cofiles.stat"), "wb").write(bytes(raw))
     r = subprocess.run([CLI, "dist", "-r", rd, "-o", os.path.join(str(tmp_path), "o2"), qd], capture_output=True, text=True)
     assert r.returncode != 0 and "shuf_id" in r.stderr
+
+
+@pytest.mark.skipif(os.environ.get("MK_TEST_MCO_DB") != "1", reason="opt-in (MK_TEST_MCO_DB=1): the reference binary writes a "
+                    "32 GiB mco.index.0 and needs two minutes for it")
+def test_cli_searches_a_database_built_by_the_reference(oracle, tmp_path):
+    """A directory that holds only what the reference leaves in a database (mcofiles.stat, mco.0, mco.index.0): the host
+    reads the inverted index back (read_mco_component) and distance.out equals the reference's own."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/metakssd is not built")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "host")], check=True, capture_output=True)
+    (k, subk, L, seed), named, ref_names, qry_names, _ = G.dist_search_case()
+    d = str(tmp_path)
+    sid, perm = oracle.make_shuf(seed, k, subk, L)
+    oracle.write_shuf_file(os.path.join(d, "x.shuf"), sid, k, subk, L, perm)
+    for n, g in named.items():
+        open(os.path.join(d, n), "wb").write(g)
+    oracle.ref_dist(os.path.join(d, "x.shuf"), [os.path.join(d, n) for n in ref_names], os.path.join(d, "ref"), abundance=False, p=1)
+    oracle.ref_dist(os.path.join(d, "x.shuf"), [os.path.join(d, n) for n in qry_names], os.path.join(d, "qry"), abundance=False, p=1)
+    want = oracle.ref_dist_search(os.path.join(d, "ref"), os.path.join(d, "qry"), os.path.join(d, "out_ref"))
+    for f in ("combco.0", "combco.index.0", "cofiles.stat"):
+        os.remove(os.path.join(d, "ref", f))
+    subprocess.run([CLI, "dist", "-r", os.path.join(d, "ref"), "-o", os.path.join(d, "out"), os.path.join(d, "qry")], check=True,
+                   capture_output=True, timeout=600)
+    assert open(os.path.join(d, "out", "distance.out")).read() == want

@@ -173,3 +173,46 @@ def test_balanced_shares_keep_the_total_and_equalise_the_ranks():
     assert D.balanced_shares(per, 1, [0.0], ms_per_read) == ([per], 0)
     shares, moved = D.balanced_shares(per, 4, [0.0, 100.0, 100.0, 100.0], ms_per_read)        # capped at 40 % of a shard
     assert moved == per * 2 // 5 and sum(shares) == 4 * per
+
+
+def test_host_reads_the_reference_mco_format(tmp_path, lib_built):
+    """host/mkssd_main.c::read_mco_component: a database directory in the reference's format (mcofiles.stat, mco.<c> =
+    the references holding each code, mco.index.<c> = END offset of every code's row, co2mco.c:56-79) comes back as
+    the sketches it was built from (`dist -r <db> --dump-ref <dir>`, no device needed).  The real index has 2^32 rows
+    (32 GiB); the reader takes as many rows as the file holds, so the test uses codes below 2^16."""
+    import os
+    import struct
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "host")], check=True, capture_output=True)
+    rng = np.random.default_rng(8)
+    n_ref, rows = 9, 1 << 16
+    sks = [np.unique(rng.integers(0, rows, size=int(rng.integers(0, 900)))).astype(np.uint32) for _ in range(n_ref)]
+    sks[3] = np.zeros(0, np.uint32)                                      # an empty sketch
+    db, qd = tmp_path / "db", tmp_path / "qry"
+    db.mkdir(); qd.mkdir()
+    names = [b"genome_%d.fa" % i for i in range(n_ref)]
+    stat_tail = np.array([s.size for s in sks], dtype=np.uint32).tobytes() + b"".join(n.ljust(256, b"\0") for n in names)
+    (db / "mcofiles.stat").write_bytes(struct.pack("<Iiiii", 77, 22, 6, 1, n_ref) + stat_tail)
+    holders = [[] for _ in range(rows)]                                  # the inverted index, rows in code order
+    for g, s in enumerate(sks):
+        for c in s:
+            holders[int(c)].append(g)
+    np.array([g for h in holders for g in h], dtype=np.uint32).tofile(db / "mco.0")
+    np.cumsum([len(h) for h in holders]).astype(np.uint64).tofile(db / "mco.index.0")
+    (qd / "cofiles.stat").write_bytes(struct.pack("<I?3xiiiiQ", 77, False, 22, 6, 1, 1, 0) + struct.pack("<I", 0) + b"q".ljust(256, b"\0"))
+    np.zeros(0, np.uint32).tofile(qd / "combco.0")
+    np.zeros(2, np.uint64).tofile(qd / "combco.index.0")
+    dump = tmp_path / "dump"
+    r = subprocess.run([os.path.join(root, "host", "metakssd-b200"), "dist", "-r", str(db), "-o", str(tmp_path / "o"),
+                        "--dump-ref", str(dump), str(qd)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    hdr, got_names, combco, index, _ = lib_built.read_sketch_dir(str(dump))
+    assert got_names == [n.decode() for n in names] and hdr["shuf_id"] == 77 and hdr["infile_num"] == n_ref
+    for g, s in enumerate(sks):
+        assert np.array_equal(combco[0][int(index[0][g]):int(index[0][g + 1])], s), g
+    # a truncated gid file is refused, not read past
+    (db / "mco.0").write_bytes((db / "mco.0").read_bytes()[:-8])
+    r = subprocess.run([os.path.join(root, "host", "metakssd-b200"), "dist", "-r", str(db), "-o", str(tmp_path / "o"),
+                        "--dump-ref", str(dump), str(qd)], capture_output=True, text=True)
+    assert r.returncode != 0 and "mco" in r.stderr

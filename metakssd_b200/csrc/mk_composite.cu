@@ -302,10 +302,12 @@ __device__ __forceinline__ int ref_elem(const u64 *__restrict__ keys, u64 lo, in
     return j == 0 ? n : (int)(keys[lo + (u64)j - 1] & 0xFFFFu);
 }
 
+// one warp per species (a thread per species walked its whole hit list alone: 1 ms for 5 M hits at L2K11)
 __global__ void __launch_bounds__(128)
 k_cstat(const u64 *__restrict__ keys, u64 n, int n_species, mk_species_stat *__restrict__ out)
 {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const u32 lane = threadIdx.x & 31u;
     if (s >= n_species) return;
     // [lo, hi) = entries of species s in the sorted keys
     u64 a = 0, b = n;
@@ -315,20 +317,24 @@ k_cstat(const u64 *__restrict__ keys, u64 n, int n_species, mk_species_stat *__r
     while (a < b) { u64 m = (a + b) >> 1; if ((keys[m] >> 16) <= (u64)s) a = m + 1; else b = m; }
     u64 hi = a;
     int cnt = (int)(hi - lo);
-    mk_species_stat st;
-    st.n = cnt;
-    u32 sum = 0;
-    for (u64 i = lo; i < hi; i++) sum += (u32)(keys[i] & 0xFFFFu);
-    st.sum = (int32_t)sum;
-    u32 lastsum = 0;
-    int lastn = 0;
+    u32 sum = 0;                                          // (32-bit wrap-around like the reference's int sum)
+    for (u64 i = lo + lane; i < hi; i += 32) sum += (u32)(keys[i] & 0xFFFFu);
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    u32 lastsum = 0, lastn = 0;
     int j0 = (int)(cnt * 0.98);
-    for (int j = j0; (double)j <= cnt * 0.99; j++) { lastsum += (u32)ref_elem(keys, lo, cnt, j); lastn++; }
-    st.lastsum = (int32_t)lastsum;
-    st.lastn = lastn;
-    st.median = cnt ? ref_elem(keys, lo, cnt, cnt / 2) : 0;
-    st.max = cnt ? ref_elem(keys, lo, cnt, cnt) : 0;
-    out[s] = st;
+    for (int j = j0 + (int)lane; (double)j <= cnt * 0.99; j += 32) { lastsum += (u32)ref_elem(keys, lo, cnt, j); lastn++; }
+    lastsum = __reduce_add_sync(0xffffffffu, lastsum);
+    lastn = __reduce_add_sync(0xffffffffu, lastn);
+    if (lane == 0) {
+        mk_species_stat st;
+        st.n = cnt;
+        st.sum = (int32_t)sum;
+        st.lastsum = (int32_t)lastsum;
+        st.lastn = (int)lastn;
+        st.median = cnt ? ref_elem(keys, lo, cnt, cnt / 2) : 0;
+        st.max = cnt ? ref_elem(keys, lo, cnt, cnt) : 0;
+        out[s] = st;
+    }
 }
 
 extern "C" int mk_composite_stats(mk_ctx *ctx, mk_species_stat *stats)
@@ -356,7 +362,7 @@ extern "C" int mk_composite_stats(mk_ctx *ctx, mk_species_stat *stats)
     for (u64 v = (u64)(S - 1); v; v >>= 1) sb++;
     u64 *sk = k0, *sv = v0;
     CKR(mk_radix_sort_pairs(ctx, &sk, &sv, k1, v1, n, 0, 16 + sb));
-    k_cstat<<<(S + 127) / 128, 128, 0, ctx->stream>>>(sk, n, S, d_out);
+    k_cstat<<<(unsigned)(((u64)S * 32 + 127) / 128), 128, 0, ctx->stream>>>(sk, n, S, d_out);
     LAUNCH_COUNT(ctx);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(stats, d_out, sizeof(mk_species_stat) * (size_t)S, cudaMemcpyDeviceToHost, ctx->stream));

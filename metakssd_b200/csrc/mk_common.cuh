@@ -107,6 +107,7 @@ struct mk_ctx {
     std::vector<cudaEvent_t> chunk_ev;
     u64 h_maxpos = 0;                     // read-back slot of mk_runs_finalize_device
     cudaEvent_t evx[2] = {nullptr, nullptr};   // around the first exchange of the sharded step
+    bool classic_only = false;            // k_stream_ws's shared-memory base assumption failed on this driver: unit-pulling kernel
     u64 last_block_need = 0;              // largest block the last sharded step saw on this rank (sent to it, or merged by it)
     u64 h_xflag = 0;                      // read-back slot of the sharded step's collective overflow flag
     u64 last_newlines = 0;                // line_base + newlines of the shard mk_fastq_partial_device saw last

@@ -1534,8 +1534,8 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
     // MK_STREAM_IMPL selects the kernel: default k_stream_ws (warp-specialised ring); "v3" = k_stream3 (front
     // end ahead of the ring, mk_stream3.cu) and "classic" = the unit-pulling kernel, both kept as cross-checks
     const char *impl = getenv("MK_STREAM_IMPL");
-    const bool v3 = impl && !strcmp(impl, "v3");
-    const bool ws = v3 || !(impl && !strcmp(impl, "classic"));      // (v3 shares the chunked-upload path with ws)
+    const bool v3 = !ctx->classic_only && impl && !strcmp(impl, "v3");
+    const bool ws = !ctx->classic_only && (v3 || !(impl && !strcmp(impl, "classic")));      // (v3 shares the chunked-upload path with ws)
     stream_kernel_t kern = v3 ? nullptr : (ws ? pick_kernel_ws(kp, raw_mode) : pick_kernel(kp, raw_mode));
     if (!kern && !v3) {
         snprintf(ctx->err, sizeof(ctx->err), "unsupported inner substring width subk=%d", kp.subk);
@@ -1721,10 +1721,20 @@ int mk_stream_fastq(mk_ctx *ctx, const uint8_t *d_text, size_t nbytes, u64 pos_b
                      (unsigned long long)((h[15] >> 21) & 0x1FFFFF), (unsigned long long)(h[15] & 0x1FFFFF), n_tiles);
             return MK_ERR_CUDA;
         }
+        if (ws && !v3 && !ctx->classic_only && getenv("MK_DEBUG_FORCE_SMEM_BASE_FLAG")) flags |= FLAG_SMEM_BASE;   // (tests: take the fallback)
         if (flags & FLAG_SMEM_BASE) {
-            snprintf(ctx->err, sizeof(ctx->err), "k_stream_ws: dynamic shared memory does not start at CTA-shared address %d "
-                     "(rebuild with -DWS_FIXED_FILTER_BASE=false)", MK_DYN_SMEM_BASE);
-            return MK_ERR_UNSUPPORTED;
+            // This driver places dynamic shared memory elsewhere: the lookups of this launch read the wrong words.
+            // The unit-pulling kernel addresses the filter through the generic pointer: use it from now on (slower,
+            // same results; -DWS_FIXED_FILTER_BASE=false rebuilds k_stream_ws without the assumption).
+            if (ctx->classic_only) {
+                snprintf(ctx->err, sizeof(ctx->err), "k_stream: shared-memory base check failed twice");
+                return MK_ERR_UNSUPPORTED;
+            }
+            fprintf(stderr, "mkssd_b200: dynamic shared memory does not start at CTA-shared address %d on this driver; "
+                            "using the unit-pulling stream kernel (rebuild with -DWS_FIXED_FILTER_BASE=false for k_stream_ws)\n",
+                    MK_DYN_SMEM_BASE);
+            ctx->classic_only = true;
+            return mk_stream_fastq(ctx, d_text, nbytes, pos_base, line_base, raw_mode, d_cand_code, d_cand_pos, n_cand, n_newlines);
         }
         if (v3 && (flags & FLAG_ARENA_FULL)) {       // unusually many short sequence lines: the cursor says what is needed
             arena_items = (size_t)h[7] + 1024;

@@ -325,3 +325,25 @@ def test_classic_stream_kernel_agrees(oracle, sk311, monkeypatch):
     monkeypatch.delenv("MK_STREAM_IMPL")
     same_sketch(s.fastq_koc_host(text), want, p)
 
+
+
+def test_fallback_when_the_shared_memory_base_check_fails(lib_built, oracle, shuf, capfd):
+    """k_stream_ws reads the filter through a fixed CTA-shared address and checks the assumption in every launch; when
+    the check fails (forced here) the context switches to the unit-pulling kernel for good and says so once."""
+    import os
+    sid, perm = shuf(1234, 11, 6, 3)
+    p = oracle.params(11, 6, 3)
+    text = oracle.synth(5, 6, 100_000, 150).fastq(0, 20_000)
+    want = oracle.fastq_koc(p, perm, text)
+    os.environ["MK_DEBUG_FORCE_SMEM_BASE_FLAG"] = "1"
+    try:
+        with lib_built.Sketcher(perm, 11, 6, 3) as sk:
+            got = sk.fastq_koc_host(np.asarray(text))
+            again = sk.fastq_koc_host(np.asarray(text))
+    finally:
+        del os.environ["MK_DEBUG_FORCE_SMEM_BASE_FLAG"]
+    err = capfd.readouterr().err
+    assert err.count("using the unit-pulling stream kernel") == 1
+    for g in (got, again):
+        comps = want.components(p)
+        assert np.array_equal(g.codes[0], comps[0][0]) and np.array_equal(g.counts[0], comps[0][1])

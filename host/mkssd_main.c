@@ -19,6 +19,7 @@
  * library is driven from one host thread).
  */
 #define _GNU_SOURCE
+#include <dirent.h>
 #include <errno.h>
 #include <math.h>
 #include <stdbool.h>
@@ -128,6 +129,56 @@ static int cmd_shuffle(int argc, char **argv)
 }
 
 /* ---- dist ------------------------------------------------------------------------------------ */
+/* Input arguments like the reference takes them (organize_infile_frm_arg() / organize_infile_list(), global_basic.c:169-330):
+ * a directory stands for the sequence files in it (one level, accepted extensions fna fas fasta fa fq fastq, optionally
+ * .gz / .bz2), `-l <file>` names one input per line.  The reference then processes the files in a time-seeded random order;
+ * here directory entries are taken in name order, so that two runs write the same sketch directory. */
+static const char *const seq_ext[] = {"fna", "fas", "fasta", "fa", "fq", "fastq", NULL};
+static int by_name(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
+static void add_input(char ***list, int *n, int *cap, const char *path)
+{
+    if (*n + 1 >= *cap) { *cap = *cap ? *cap * 2 : 64; *list = realloc(*list, sizeof(char *) * (size_t)*cap); }
+    (*list)[(*n)++] = strdup(path);
+}
+static void expand_input(char ***list, int *n, int *cap, const char *arg)
+{
+    struct stat st;
+    if (stat(arg, &st) == 0 && S_ISDIR(st.st_mode)) {
+        DIR *d = opendir(arg);
+        if (!d) die("cannot open directory", arg);
+        int first = *n;
+        struct dirent *e;
+        while ((e = readdir(d)) != NULL) {
+            char full[PATHLEN * 2];
+            snprintf(full, sizeof full, "%s/%s", arg, e->d_name);
+            if (strlen(full) >= PATHLEN) die("path exceeds the maximal path length", full);
+            if (stat(full, &st) == 0 && S_ISREG(st.st_mode) && has_ext(full, seq_ext)) add_input(list, n, cap, full);
+        }
+        closedir(d);
+        qsort(*list + first, (size_t)(*n - first), sizeof(char *), by_name);
+    } else {
+        add_input(list, n, cap, arg);
+    }
+}
+static void expand_list_file(char ***list, int *n, int *cap, const char *path)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) die("can't open file", path);
+    char line[PATHLEN * 4];
+    while (fgets(line, sizeof line, f)) {
+        char *p = line;
+        while (*p == ' ' || *p == '\t') p++;
+        p[strcspn(p, "\r\n")] = 0;
+        if (!*p) continue;
+        if (strlen(p) >= PATHLEN) die("a line of the input list exceeds the maximal path length", path);
+        struct stat st;
+        if (stat(p, &st) || !S_ISREG(st.st_mode)) die("not a file (input list)", p);
+        if (!has_ext(p, seq_ext)) die("wrong format in the input list (supported: .fna .fas .fasta .fq .fastq .fa)", p);
+        add_input(list, n, cap, p);
+    }
+    fclose(f);
+}
+
 /* ---- dist -r <ref> -o <out> <qry>: shared k-mer counts + distance table ---------------------------------
  * mco_cbdco_nobin_dist() (command_dist.c:902-1079): the counts come from mk_shared_counts() (one call per component),
  * the table is dist_print_nobin() / output_ctrl() (command_dist.c:1531-1680) — four integers per pair through the same
@@ -380,8 +431,12 @@ static int cmd_dist(int argc, char **argv)
     search_opt so = {0, 2, 0, 0, 0, 1.0, NULL};      /* command_dist_wrapper.c:83-92: Jaccard, all fields, every reference, D <= 1 */
     bool abundance = false, dedup = false;
     int kmerqlty = 0, kmerocrs = 1;            /* command_dist_wrapper.c:79-80 */
-    char **inputs = malloc(sizeof(char *) * (size_t)(argc + 1));
-    int n_in = 0;
+    char **inputs = NULL;
+    int n_in = 0, cap_in = 0;
+    const char *listfile = NULL;
+    bool list_only = false;
+    char **raw = malloc(sizeof(char *) * (size_t)(argc + 1));
+    int n_raw = 0;
     for (int i = 0; i < argc; i++) {
         if (!strcmp(argv[i], "-L") && i + 1 < argc) shuf = argv[++i];
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) outdir = argv[++i];
@@ -404,8 +459,19 @@ static int cmd_dist(int argc, char **argv)
             if (v < 1) { fprintf(stderr, "metakssd-b200: -n argument is smaller than Min, it has been set to 1, ignorned -n %d \n", v); v = 1; }
             kmerocrs = v;
         }
+        else if (!strcmp(argv[i], "-l") && i + 1 < argc) listfile = argv[++i];
+        else if (!strcmp(argv[i], "--list-inputs")) list_only = true;        /* (tool: print the expanded inputs and leave) */
         else if (argv[i][0] == '-') die("option not on the hot path", argv[i]);
-        else inputs[n_in++] = argv[i];
+        else raw[n_raw++] = argv[i];
+    }
+    for (int i = 0; i < n_raw; i++) {
+        if (refpath) add_input(&inputs, &n_in, &cap_in, raw[i]);            /* (the query of dist -r is a sketch directory) */
+        else expand_input(&inputs, &n_in, &cap_in, raw[i]);
+    }
+    if (listfile) expand_list_file(&inputs, &n_in, &cap_in, listfile);
+    if (list_only) {
+        for (int i = 0; i < n_in; i++) printf("%s\n", inputs[i]);
+        return 0;
     }
     if (refpath) {            /* database search: the query is a sketch directory (command_dist.c:152-171) */
         if (n_in != 1) die("dist -r takes one query sketch directory", NULL);

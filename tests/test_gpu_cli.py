@@ -74,3 +74,27 @@ def test_cli_reports_crowded_like_the_reference(cli, oracle, lib_built, tmp_path
     r = subprocess.run([CLI, "dist", "-L", str(tmp_path / "x.shuf"), "-A", "-o", str(tmp_path / "o"), str(fq)],
                        capture_output=True, text=True, timeout=300)
     assert r.returncode != 0 and "too crowd" in r.stderr and "-k8" in r.stderr
+
+
+def test_cli_dist_takes_a_directory_and_a_list_file(cli, oracle, tmp_path):
+    """A directory argument and `-l <list>` give the sketch directory the explicit file arguments give
+    (organize_infile_frm_arg / organize_infile_list, global_basic.c:169-330)."""
+    S = oracle.synth(9, 6, 120_000, 150)
+    _run("shuffle", "-k", 11, "-s", 6, "-l", 3, "-o", tmp_path / "L3K11", "--seed", 5)
+    shuf = tmp_path / "L3K11.shuf"
+    g = tmp_path / "genomes"
+    g.mkdir()
+    paths = []
+    for s in range(6):
+        fa = g / ("sp%d.fasta" % s)
+        S.fasta(s).tofile(fa)
+        paths.append(str(fa))
+    (g / "README.txt").write_text("not a sequence file")
+    (tmp_path / "list.txt").write_text("\n".join(paths) + "\n")
+    _run("dist", "-L", shuf, "-o", tmp_path / "by_files", *paths)
+    _run("dist", "-L", shuf, "-o", tmp_path / "by_dir", g)
+    _run("dist", "-L", shuf, "-o", tmp_path / "by_list", "-l", tmp_path / "list.txt")
+    want = [open(tmp_path / "by_files" / f, "rb").read() for f in ("combco.0", "combco.index.0", "cofiles.stat")]
+    for d in ("by_dir", "by_list"):
+        assert [open(tmp_path / d / f, "rb").read() for f in ("combco.0", "combco.index.0", "cofiles.stat")] == want, d
+    assert len(want[0]) > 4 * 100

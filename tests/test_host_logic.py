@@ -216,3 +216,29 @@ def test_host_reads_the_reference_mco_format(tmp_path, lib_built):
     r = subprocess.run([os.path.join(root, "host", "metakssd-b200"), "dist", "-r", str(db), "-o", str(tmp_path / "o"),
                         "--dump-ref", str(dump), str(qd)], capture_output=True, text=True)
     assert r.returncode != 0 and "mco" in r.stderr
+
+
+def test_host_dist_expands_directories_and_list_files(tmp_path):
+    """`dist` takes its inputs like the reference (organize_infile_frm_arg / organize_infile_list, global_basic.c:169-330):
+    a directory stands for the sequence files in it (accepted extensions, optionally compressed), -l names one file per
+    line; `--list-inputs` prints the expansion without touching a device.  The query of `dist -r` is left alone."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "host")], check=True, capture_output=True)
+    cli = os.path.join(root, "host", "metakssd-b200")
+    g = tmp_path / "genomes"
+    g.mkdir()
+    for n in ("b.fasta", "a.fq.gz", "notes.txt", "d.FA", "e.fna.bz2", "sub"):
+        (g / n).mkdir() if n == "sub" else (g / n).write_bytes(b"")
+    lst = tmp_path / "list.txt"
+    lst.write_text("  %s\n\n%s\r\n" % (g / "b.fasta", g / "a.fq.gz"))
+    r = subprocess.run([cli, "dist", "--list-inputs", str(g), str(g / "d.FA"), "-l", str(lst)], capture_output=True, text=True, check=True)
+    want = [str(g / n) for n in ("a.fq.gz", "b.fasta", "d.FA", "e.fna.bz2")] + [str(g / "d.FA"), str(g / "b.fasta"), str(g / "a.fq.gz")]
+    assert r.stdout.split("\n")[:-1] == want
+    r = subprocess.run([cli, "dist", "--list-inputs", str(g), "-r", "refdir", "-o", "out"], capture_output=True, text=True, check=True)
+    assert r.stdout == str(g) + "\n"
+    bad = tmp_path / "bad.txt"
+    bad.write_text(str(g / "notes.txt") + "\n")
+    r = subprocess.run([cli, "dist", "--list-inputs", "-l", str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "wrong format" in r.stderr

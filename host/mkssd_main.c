@@ -187,7 +187,7 @@ static void expand_list_file(char ***list, int *n, int *cap, const char *path)
  * needed nor written. */
 typedef struct { unsigned int shuf_id; int kmerlen, dim_rd_len, comp_num, infile_num; } mco_dstat_t;   /* command_dist.h:67-75 */
 static mk_ctx *plain_ctx(const co_dstat_t *st);
-typedef struct { int metric, outfields, correction, n_max, keep; double max_dist; const char *dump_ref; } search_opt;
+typedef struct { int metric, outfields, correction, n_max, keep; double max_dist; const char *dump_ref, *skf; } search_opt;
 
 static int dist_line(char *line, size_t cap, const search_opt *o, int kmerlen, int dim_rd_len, const char *qname,
                      const char *rname, unsigned X, unsigned Y, unsigned XnY, double n_cmp)
@@ -346,30 +346,38 @@ static int dist_search(const char *refdir, const char *qrydir, const char *outdi
         phase("dump reference side");
         return 0;
     }
-    co_dstat_t geo = Q;
-    mk_ctx *ctx = plain_ctx(&geo);
-    phase("mk_ctx_create");
-    uint32_t *counts = calloc((size_t)n_ref * (size_t)n_qry, sizeof *counts);
-    if (!counts) die("out of memory for the shared k-mer count matrix", NULL);
-    for (int c = 0; c < R.comp_num; c++) {
+    mk_ctx *ctx = NULL;
+    uint32_t *counts;
+    if (o->skf) {               /* the counts of an earlier run (--keepskf): only the table is printed, no device needed */
         size_t b;
-        uint32_t *rc;
-        uint64_t *ri;
-        snprintf(path, sizeof path, "%s/combco.%d", refdir, c);
-        if (stat(path, &sb) == 0) {
-            rc = slurp(path, &b);
-            snprintf(path, sizeof path, "%s/combco.index.%d", refdir, c);
-            ri = slurp(path, &b);
-        } else {                              /* a database built by the reference: only its inverted index is there */
-            read_mco_component(refdir, c, n_ref, &rc, &ri);
-            phase("read mco index");
+        counts = slurp(o->skf, &b);
+        if (b != (size_t)n_ref * (size_t)n_qry * sizeof *counts) die("the shared k-mer count file does not fit these directories", o->skf);
+    } else {
+        co_dstat_t geo = Q;
+        ctx = plain_ctx(&geo);
+        phase("mk_ctx_create");
+        counts = calloc((size_t)n_ref * (size_t)n_qry, sizeof *counts);
+        if (!counts) die("out of memory for the shared k-mer count matrix", NULL);
+        for (int c = 0; c < R.comp_num; c++) {
+            size_t b;
+            uint32_t *rc;
+            uint64_t *ri;
+            snprintf(path, sizeof path, "%s/combco.%d", refdir, c);
+            if (stat(path, &sb) == 0) {
+                rc = slurp(path, &b);
+                snprintf(path, sizeof path, "%s/combco.index.%d", refdir, c);
+                ri = slurp(path, &b);
+            } else {                              /* a database built by the reference: only its inverted index is there */
+                read_mco_component(refdir, c, n_ref, &rc, &ri);
+                phase("read mco index");
+            }
+            snprintf(path, sizeof path, "%s/combco.%d", qrydir, c);
+            uint32_t *qc = slurp(path, &b);
+            snprintf(path, sizeof path, "%s/combco.index.%d", qrydir, c);
+            uint64_t *qi = slurp(path, &b);
+            ck(ctx, mk_shared_counts(ctx, rc, ri, n_ref, qc, qi, n_qry, q_ct, counts), "mk_shared_counts");
+            free(rc); free(ri); free(qc); free(qi);
         }
-        snprintf(path, sizeof path, "%s/combco.%d", qrydir, c);
-        uint32_t *qc = slurp(path, &b);
-        snprintf(path, sizeof path, "%s/combco.index.%d", qrydir, c);
-        uint64_t *qi = slurp(path, &b);
-        ck(ctx, mk_shared_counts(ctx, rc, ri, n_ref, qc, qi, n_qry, q_ct, counts), "mk_shared_counts");
-        free(rc); free(ri); free(qc); free(qi);
     }
     phase("shared k-mer counts");
     mkdir(outdir, 0700);
@@ -420,7 +428,7 @@ static int dist_search(const char *refdir, const char *qrydir, const char *outdi
     }
     fclose(f);
     phase("distance.out");
-    mk_ctx_destroy(ctx);
+    if (ctx) mk_ctx_destroy(ctx);
     free(best); free(counts); free(raw); free(qraw);
     return 0;
 }
@@ -428,7 +436,7 @@ static int dist_search(const char *refdir, const char *qrydir, const char *outdi
 static int cmd_dist(int argc, char **argv)
 {
     const char *shuf = NULL, *outdir = "./", *pipecmd = "", *refpath = NULL;
-    search_opt so = {0, 2, 0, 0, 0, 1.0, NULL};      /* command_dist_wrapper.c:83-92: Jaccard, all fields, every reference, D <= 1 */
+    search_opt so = {0, 2, 0, 0, 0, 1.0, NULL, NULL};      /* command_dist_wrapper.c:83-92: Jaccard, all fields, every reference, D <= 1 */
     bool abundance = false, dedup = false;
     int kmerqlty = 0, kmerocrs = 1;            /* command_dist_wrapper.c:79-80 */
     char **inputs = NULL;
@@ -451,6 +459,7 @@ static int cmd_dist(int argc, char **argv)
         else if (!strcmp(argv[i], "-D") && i + 1 < argc) so.max_dist = atof(argv[++i]);
         else if (!strcmp(argv[i], "--correction") && i + 1 < argc) so.correction = atoi(argv[++i]);
         else if (!strcmp(argv[i], "--keepskf")) so.keep = 1;
+        else if (!strcmp(argv[i], "-f") && i + 1 < argc) so.skf = argv[++i];      /* print from a kept sharedk_ct.dat (command_dist.c:984-987) */
         else if (!strcmp(argv[i], "--dump-ref") && i + 1 < argc) so.dump_ref = argv[++i];   /* (tool: the reference side as a sketch directory) */
         else if (!strcmp(argv[i], "-Q") && i + 1 < argc) kmerqlty = atoi(argv[++i]);
         else if (!strcmp(argv[i], "-n") && i + 1 < argc) {        /* clamped to 1..7 like command_dist_wrapper.c:169-179 */

@@ -58,6 +58,21 @@ def main():
         out["outA/default"] = np.array(O.ref_dist_search("ref", "qryA", "outA"))
         O.ref_dist_search("ref", "qryA", "outA_keep", extra=["--keepskf"])
         out["sharedk_ct_A"] = np.fromfile("outA_keep/sharedk_ct.dat", dtype=np.uint32).reshape(1, len(ref_names))
+        # edge: sketches without a single code on both sides (Jaccard 0/0, containment x/0 ...)
+        with open("tiny_a.fasta", "wb") as f:
+            f.write(b">t\nACGTACGTAC\n")
+        with open("tiny_b.fasta", "wb") as f:
+            f.write(b">t\nTTTTGGGGCCCCAAAA\n")
+        eref = O.ref_dist(shuf, ref_names[:3] + ["tiny_a.fasta"], "eref", abundance=False, p=1)
+        eqry = O.ref_dist(shuf, [ref_names[0], "tiny_b.fasta", qry_names[-1]], "eqry", abundance=False, p=1)
+        out["edge/ref/names"] = np.array(eref.names)
+        out["edge/qry/names"] = np.array(eqry.names)
+        out["edge/ref/ctx_ct"] = np.asarray(eref.ctx_ct, dtype=np.uint32)
+        out["edge/qry/ctx_ct"] = np.asarray(eqry.ctx_ct, dtype=np.uint32)
+        for name in ("default", "containment", "nearest3", "corrected"):
+            out["edge/out/" + name] = np.array(O.ref_dist_search("eref", "eqry", "eout_" + name, extra=G.DIST_SEARCH_OPTIONS[name]))
+        O.ref_dist_search("eref", "eqry", "eout_keep", extra=["--keepskf"])
+        out["edge/sharedk_ct"] = np.fromfile("eout_keep/sharedk_ct.dat", dtype=np.uint32).reshape(3, 4)
         os.chdir(cwd)
     np.savez_compressed(os.path.join(HERE, "reference_vectors_r2b.npz"), **out)
     print("wrote", len(out), "arrays")

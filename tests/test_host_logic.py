@@ -242,3 +242,38 @@ def test_host_dist_expands_directories_and_list_files(tmp_path):
     bad.write_text(str(g / "notes.txt") + "\n")
     r = subprocess.run([cli, "dist", "--list-inputs", "-l", str(bad)], capture_output=True, text=True)
     assert r.returncode != 0 and "wrong format" in r.stderr
+
+
+def test_host_prints_the_reference_distance_table(tmp_path, lib_built, oracle):
+    """host/mkssd_main.c::dist_search printing (dist_print_nobin / output_ctrl, command_dist.c:1531-1680) on CPU: with
+    `-f <sharedk_ct.dat>` the table is printed from a kept count matrix (command_dist.c:984-987), so the golden matrix of
+    the reference binary must give the reference's distance.out for all eight option sets, byte for byte."""
+    import os
+    import subprocess
+    import golden_cases as G
+    from helpers import dist_search_world
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-C", os.path.join(root, "host")], check=True, capture_output=True)
+    cli = os.path.join(root, "host", "metakssd-b200")
+    gold = np.load(os.path.join(root, "tests", "golden", "reference_vectors_r2b.npz"))
+    p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct = dist_search_world(oracle, gold)
+    sid = oracle.make_shuf(1234, 11, 6, 3)[0]
+    info = lib_built.MkInfo()
+    info.k, info.drlevel, info.component_num = 11, 3, 1
+
+    def sketches(side):
+        codes, idx = side
+        return [lib_built.Sketch([codes[int(idx[i]):int(idx[i + 1])]], None) for i in range(idx.size - 1)]
+
+    rd, qd = str(tmp_path / "ref"), str(tmp_path / "qry")
+    lib_built.write_sketch_dir(rd, sid, info, ref_names, sketches(ref), False)
+    lib_built.write_sketch_dir(qd, sid, info, qry_names, sketches(qry), False)
+    skf = str(tmp_path / "sharedk_ct.dat")
+    gold["sharedk_ct"].astype(np.uint32).tofile(skf)
+    for name, flags in G.DIST_SEARCH_OPTIONS.items():
+        out = str(tmp_path / ("out_" + name))
+        subprocess.run([cli, "dist", "-r", rd, "-o", out, "-f", skf] + flags + [qd], check=True, capture_output=True, timeout=60)
+        assert open(os.path.join(out, "distance.out")).read() == str(gold["out/" + name]), name
+    open(skf, "ab").write(b"\0\0\0\0")
+    r = subprocess.run([cli, "dist", "-r", rd, "-o", str(tmp_path / "o"), "-f", skf, qd], capture_output=True, text=True)
+    assert r.returncode != 0 and "does not fit" in r.stderr

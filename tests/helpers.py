@@ -49,3 +49,27 @@ def dist_search_world(oracle, gold):
     ref, ref_ct = side(ref_names)
     qry, qry_ct = side(qry_names)
     return p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct
+
+
+def dist_search_edge_world(oracle, gold):
+    """The edge case of the `dist -r` vectors: a reference and a query sketch without a single code."""
+    import golden_cases as G
+    import numpy as np
+    (k, subk, L, seed), named, _, _, _ = G.dist_search_case()
+    named = dict(named)
+    named["tiny_a.fasta"] = b">t\nACGTACGTAC\n"
+    named["tiny_b.fasta"] = b">t\nTTTTGGGGCCCCAAAA\n"
+    p = oracle.params(k, subk, L)
+    _, perm = oracle.make_shuf(seed, k, subk, L)
+
+    def side(names):
+        sk = [oracle.fasta_co(p, perm, named[n]).components(p)[0][0] for n in names]
+        index = np.zeros(len(sk) + 1, dtype=np.uint64)
+        index[1:] = np.cumsum([s.size for s in sk])
+        return (np.concatenate(sk).astype(np.uint32), index), np.array([s.size for s in sk], dtype=np.uint32)
+
+    ref_names = [str(n) for n in gold["edge/ref/names"]]
+    qry_names = [str(n) for n in gold["edge/qry/names"]]
+    ref, ref_ct = side(ref_names)
+    qry, qry_ct = side(qry_names)
+    return p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct

@@ -28,6 +28,14 @@ def test_shared_counts_against_the_reference_matrix(lib_built, oracle, shuf):
         assert np.array_equal(sk.shared_counts([ref], [qa], gold["qryA/ctx_ct"]), gold["sharedk_ct_A"])
 
 
+def test_shared_counts_with_empty_sketches(lib_built, oracle):
+    from helpers import dist_search_edge_world
+    gold = np.load(GOLD)
+    p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct = dist_search_edge_world(oracle, gold)
+    with lib_built.Sketcher(None, 11, 6, 3) as sk:
+        assert np.array_equal(sk.shared_counts([ref], [qry], qry_ct), gold["edge/sharedk_ct"])
+
+
 def test_shared_counts_random_against_oracle(lib_built, oracle):
     """Random sketches: many references sharing codes, empty sketches, a query whose ctx_ct is 0 (skipped like
     command_dist.c:1033), several components accumulating into one matrix; a context without a .shuf is enough."""

@@ -277,3 +277,15 @@ def test_host_prints_the_reference_distance_table(tmp_path, lib_built, oracle):
     open(skf, "ab").write(b"\0\0\0\0")
     r = subprocess.run([cli, "dist", "-r", rd, "-o", str(tmp_path / "o"), "-f", skf, qd], capture_output=True, text=True)
     assert r.returncode != 0 and "does not fit" in r.stderr
+    # sketches without a code: the nan / inf lines of the reference
+    from helpers import dist_search_edge_world
+    p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct = dist_search_edge_world(oracle, gold)
+    rd, qd = str(tmp_path / "eref"), str(tmp_path / "eqry")
+    lib_built.write_sketch_dir(rd, sid, info, ref_names, sketches(ref), False)
+    lib_built.write_sketch_dir(qd, sid, info, qry_names, sketches(qry), False)
+    gold["edge/sharedk_ct"].astype(np.uint32).tofile(skf)
+    for name in ("default", "containment", "nearest3", "corrected"):
+        out = str(tmp_path / ("eout_" + name))
+        subprocess.run([cli, "dist", "-r", rd, "-o", out, "-f", skf] + G.DIST_SEARCH_OPTIONS[name] + [qd], check=True,
+                       capture_output=True, timeout=60)
+        assert open(os.path.join(out, "distance.out")).read() == str(gold["edge/out/" + name]), name

@@ -115,3 +115,19 @@ def test_dist_search_golden(oracle):
     assert np.array_equal(ca, gold["sharedk_ct_A"])
     txt = oracle.distance_out(ca, ref_ct, gold["qryA/ctx_ct"], ref_names, ["reads.fq"], 2 * p.k, 2 * p.drlevel)
     assert txt == str(gold["outA/default"])
+
+
+def test_dist_search_golden_empty_sketches(oracle):
+    """Sketches without a code on either side: 0/0 and x/0 go through the same libm calls and printf formats as in the
+    reference (`-nan`, `-NAN`, `inf`), and such lines are printed (NaN > max_dist is false)."""
+    from helpers import dist_search_edge_world
+    gold = np.load(GOLD_B)
+    p, perm, ref_names, ref, ref_ct, qry_names, qry, qry_ct = dist_search_edge_world(oracle, gold)
+    assert np.array_equal(ref_ct, gold["edge/ref/ctx_ct"]) and np.array_equal(qry_ct, gold["edge/qry/ctx_ct"])
+    assert 0 in ref_ct and 0 in qry_ct
+    counts = oracle.shared_counts([ref], [qry], qry_ct)
+    assert np.array_equal(counts, gold["edge/sharedk_ct"])
+    for name in ("default", "containment", "nearest3", "corrected"):
+        txt = oracle.distance_out(counts, ref_ct, qry_ct, ref_names, qry_names, 2 * p.k, 2 * p.drlevel, **_opts(G.DIST_SEARCH_OPTIONS[name]))
+        assert txt == str(gold["edge/out/" + name]), name
+        assert name == "nearest3" or "nan" in txt          # (the N-nearest selection never picks a NaN metric)

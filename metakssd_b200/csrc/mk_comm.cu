@@ -4,15 +4,18 @@
 // The reference is a single process (no counterpart); what is reproduced is its RESULT on the whole file:
 //   * reads are sharded by contiguous record ranges; every rank reduces its shard to runs
 //     (code, first global position, count) sorted by code — mk_fastq_partial_device;
-//   * the code space [0, 2^code_bits) is cut into `world` equal ranges; ONE grouped ncclSend/ncclRecv step
-//     moves every run to the owner of its range.  Blocks have a fixed capacity (`max_runs` per pair) and
-//     carry their count in a header, so no size is exchanged beforehand and nothing is read back to the
-//     host before the data moves; unused slots hold an empty marker that the merge skips;
+//   * the code space [0, 2^code_bits) is cut into `world` ranges that hold the same share of the codes
+//     (quantiles of the canonical-k-mer law, range_edge()); ONE grouped ncclSend/ncclRecv step moves every
+//     run to the owner of its range.  Blocks have a fixed capacity (`max_runs` per pair) and carry their
+//     count in a header, so no size is exchanged beforehand and nothing is read back to the host before
+//     the data moves; unused slots hold an empty marker that the merge skips.  A block that does not fit
+//     fails the step on every rank together (one 8-byte all-reduce), and says how large it had to be;
 //   * the owner merges (counts add up and saturate at 65535, first position = minimum), probes ITS slice
 //     of the MarkerDB (mk_markerdb_load_sharded keeps the codes of its range) and sends rank 0 the
 //     (species, count) hits — a block whose size rank 0 knows from the load — and the merged runs;
-//   * rank 0 reproduces the reference's hash-slot order from the merged runs (the one step that needs all
-//     codes of a component in one table) and the per-species statistics from the gathered hits.
+//   * rank 0 packs the gathered blocks (distinct codes, ascending ranges: no second accumulate), reproduces
+//     the reference's hash-slot order from them (the one step that needs all codes of a component in one
+//     table) and the per-species statistics from the gathered hits.
 //
 // NCCL is loaded with dlopen("libnccl.so.2") when a communicator is first asked for: the library itself
 // has no link-time dependency on it (it loads on a CPU box, and inside a torch process it picks up the
